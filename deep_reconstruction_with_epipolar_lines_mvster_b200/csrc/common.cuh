@@ -1,0 +1,146 @@
+// Shared device/host helpers for libmvster_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mvster_b200.h"
+
+namespace mvster {
+
+// ---- host-side error plumbing (thread-local message, no exceptions across the C boundary) ------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int fail(mvster_status st, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// RAII device guard keyed on the device that owns `ptr`
+struct DeviceGuard {
+    int prev = -1;
+    int dev = -1;
+    int status = MVSTER_OK;
+    explicit DeviceGuard(const void* ptr);
+    ~DeviceGuard();
+};
+
+#define MVSTER_CHECK_LAUNCH(what)                                   \
+    do {                                                            \
+        cudaError_t e__ = cudaGetLastError();                       \
+        if (e__ != cudaSuccess) return mvster::check_cuda(e__, what); \
+    } while (0)
+
+// ---- device helpers ------------------------------------------------------------------------------------------
+struct alignas(32) F8 {
+    float v[8];
+};
+
+// 256-bit read-only global load (LDG.E.256, new on sm_100): one instruction fetches a lane's 8 fp32 channels.
+__device__ __forceinline__ F8 ldg256(const float* p) {
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                   "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
+// 8 bf16 channels (16 bytes) -> 8 floats
+__device__ __forceinline__ F8 ldg_bf16x8(const __nv_bfloat16* p) {
+    uint4 q;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p));
+    F8 r;
+    r.v[0] = __uint_as_float(q.x << 16);
+    r.v[1] = __uint_as_float(q.x & 0xffff0000u);
+    r.v[2] = __uint_as_float(q.y << 16);
+    r.v[3] = __uint_as_float(q.y & 0xffff0000u);
+    r.v[4] = __uint_as_float(q.z << 16);
+    r.v[5] = __uint_as_float(q.z & 0xffff0000u);
+    r.v[6] = __uint_as_float(q.w << 16);
+    r.v[7] = __uint_as_float(q.w & 0xffff0000u);
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ F8 load8(const T* p);
+template <>
+__device__ __forceinline__ F8 load8<float>(const float* p) {
+    return ldg256(p);
+}
+template <>
+__device__ __forceinline__ F8 load8<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return ldg_bf16x8(p);
+}
+
+// streaming (read-once) scalar load that does not allocate in L1
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+// streaming store (evict-first): outputs are consumed by the next kernel, never re-read here
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// vector reduction into global memory (no return value): RED.E.ADD.F32x4 on sm_90+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Per-(batch, view) homography [R | t], 12 floats, uniform across a CTA.
+struct Homography {
+    float r00, r01, r02, t0, r10, r11, r12, t1, r20, r21, r22, t2;
+};
+__device__ __forceinline__ Homography load_homography(const float* rt) {
+    Homography h;
+    const float4* q = reinterpret_cast<const float4*>(rt);
+    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    h.r00 = a.x; h.r01 = a.y; h.r02 = a.z; h.t0 = a.w;
+    h.r10 = b.x; h.r11 = b.y; h.r12 = b.z; h.t1 = b.w;
+    h.r20 = c.x; h.r21 = c.y; h.r22 = c.z; h.t2 = c.w;
+    return h;
+}
+
+// Bilinear footprint of one sample: 4 clamped tap offsets (in texels) and 4 weights; out-of-image taps have
+// weight 0 (grid_sample padding_mode='zeros', align_corners=True; reference models/mvs4net_utils.py:59).
+struct Taps {
+    int o00, o01, o10, o11;   // texel offsets  y*Ws + x
+    float w00, w01, w10, w11; // (row y0: x0, x0+1) (row y0+1: x0, x0+1)
+    bool any;
+};
+
+// p = R*[x,y,1]*d + t ; z==0 -> 1e-9 ; (sx,sy) = p.xy / z        (reference models/mvs4net_utils.py:42-48)
+__device__ __forceinline__ Taps make_taps(float ax, float ay, float az, const Homography& h, float d, int Hs,
+                                          int Ws) {
+    float px = fmaf(ax, d, h.t0);
+    float py = fmaf(ay, d, h.t1);
+    float pz = fmaf(az, d, h.t2);
+    pz = (pz == 0.0f) ? 1e-9f : pz;
+    float sx = __fdiv_rn(px, pz);
+    float sy = __fdiv_rn(py, pz);
+    Taps t;
+    // also false for NaN coordinates (the CPU reference samples nothing there)
+    t.any = (sx > -1.0f) && (sx < (float)Ws) && (sy > -1.0f) && (sy < (float)Hs);
+    float x0f = floorf(sx), y0f = floorf(sy);
+    float fx = sx - x0f, fy = sy - y0f;
+    int x0 = (int)x0f, y0 = (int)y0f;
+    bool vx0 = t.any && (x0 >= 0), vx1 = t.any && (x0 + 1 < Ws);
+    bool vy0 = (y0 >= 0), vy1 = (y0 + 1 < Hs);
+    int xc0 = max(x0, 0), xc1 = min(x0 + 1, Ws - 1);
+    int yc0 = max(y0, 0), yc1 = min(y0 + 1, Hs - 1);
+    if (!t.any) { xc0 = xc1 = yc0 = yc1 = 0; }
+    t.o00 = yc0 * Ws + xc0;
+    t.o01 = yc0 * Ws + xc1;
+    t.o10 = yc1 * Ws + xc0;
+    t.o11 = yc1 * Ws + xc1;
+    float gx = 1.0f - fx, gy = 1.0f - fy;
+    t.w00 = (vx0 && vy0) ? gx * gy : 0.0f;
+    t.w01 = (vx1 && vy0) ? fx * gy : 0.0f;
+    t.w10 = (vx0 && vy1) ? gx * fy : 0.0f;
+    t.w11 = (vx1 && vy1) ? fx * fy : 0.0f;
+    return t;
+}
+
+}  // namespace mvster

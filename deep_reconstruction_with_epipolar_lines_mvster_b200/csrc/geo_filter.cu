@@ -1,0 +1,312 @@
+// K2b: photometric / geometric-consistency filter of test_mvs4.py.
+//   reproject_with_depth          test_mvs4.py:612-649
+//   check_geometric_consistency   test_mvs4.py:653-670
+//   mask fusion in filter_depth   test_mvs4.py:716,738,744,746,749
+// The reference builds dense float64 NumPy temporaries per (ref, src) pair and samples the source depth with
+// cv2.remap; here one thread owns one reference pixel, walks all S source views of its reference view and keeps
+// the vote count and depth sum in registers.  The projective math stays in float64 (the 1-px / 1 % thresholds are
+// compared on float64 / float32 quantities exactly as NumPy does); the 3x3 / 3x1 matrices of every pair are
+// pre-composed in float64 on the host (they are the same np.linalg.inv / matmul products the reference forms).
+// cv2.remap(INTER_LINEAR) is emulated bit-for-bit in its coordinate handling: float32 map, fixed point with 5
+// fractional bits (round-half-even), constant-0 border.
+#include <vector>
+
+#include "common.cuh"
+
+namespace mvster {
+
+// Per-(ref, src) pair camera chain, float64:
+//   X_src  = A * ([x,y,1] * d_ref) + a          A = R_rel * K_ref^-1,      a = t_rel       (rel = E_src * E_ref^-1)
+//   q      = K_src * X_src
+//   X_ref' = Bm * ([u,v,1] * d_src) + bb        Bm = R_back * K_src^-1,    bb = t_back     (back = E_ref * E_src^-1)
+//   q'     = K_ref * X_ref'
+struct PairCam {
+    double Kri[9];   // K_ref^-1
+    double Rrel[9];  // (E_src E_ref^-1)[:3,:3]
+    double trel[3];
+    double Ks[9];
+    double Ksi[9];   // K_src^-1
+    double Rback[9];
+    double tback[3];
+    double Kr[9];
+    int src;  // source view index (into the depth stack), < 0 = skip
+    int pad;
+};
+
+__device__ __forceinline__ void mat3_vec(const double* m, double x, double y, double z, double& ox, double& oy,
+                                         double& oz) {
+    ox = m[0] * x + m[1] * y + m[2] * z;
+    oy = m[3] * x + m[4] * y + m[5] * z;
+    oz = m[6] * x + m[7] * y + m[8] * z;
+}
+
+// cv2.remap(INTER_LINEAR, BORDER_CONSTANT=0) on a float32 image: coordinates are converted to fixed point with
+// INTER_BITS=5 (cvRound = round-half-even of x*32), tap = floor, weights = (frac/32) products in float32.
+__device__ __forceinline__ float remap_linear(const float* __restrict__ img, int H, int W, float mx, float my) {
+    if (!(isfinite(mx) && isfinite(my))) return 0.0f;
+    const double xs = fmin(fmax((double)mx * 32.0, -1e8), 1e8);
+    const double ys = fmin(fmax((double)my * 32.0, -1e8), 1e8);
+    const int ix = __double2int_rn(xs);
+    const int iy = __double2int_rn(ys);
+    const int x0 = ix >> 5, y0 = iy >> 5;
+    const float fx = (float)(ix & 31) * (1.0f / 32.0f);
+    const float fy = (float)(iy & 31) * (1.0f / 32.0f);
+    if (x0 < -1 || x0 >= W || y0 < -1 || y0 >= H) return 0.0f;
+    const bool vx0 = x0 >= 0, vx1 = x0 + 1 < W, vy0 = y0 >= 0, vy1 = y0 + 1 < H;
+    const float v00 = (vx0 && vy0) ? __ldg(img + (size_t)y0 * W + x0) : 0.0f;
+    const float v01 = (vx1 && vy0) ? __ldg(img + (size_t)y0 * W + x0 + 1) : 0.0f;
+    const float v10 = (vx0 && vy1) ? __ldg(img + (size_t)(y0 + 1) * W + x0) : 0.0f;
+    const float v11 = (vx1 && vy1) ? __ldg(img + (size_t)(y0 + 1) * W + x0 + 1) : 0.0f;
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    // no FMA contraction: OpenCV multiplies by a pre-rounded float weight table and adds left to right
+    float acc = __fmul_rn(v00, __fmul_rn(gx, gy));
+    acc = __fadd_rn(acc, __fmul_rn(v01, __fmul_rn(fx, gy)));
+    acc = __fadd_rn(acc, __fmul_rn(v10, __fmul_rn(gx, fy)));
+    acc = __fadd_rn(acc, __fmul_rn(v11, __fmul_rn(fx, fy)));
+    return acc;
+}
+
+struct PairResult {
+    bool mask;
+    float depth_reprojected;  // before the [~mask] = 0 overwrite
+    float x_src, y_src;
+};
+
+__device__ __forceinline__ PairResult check_pair(const PairCam& c, const float* __restrict__ depth_src, int H, int W,
+                                                 int x, int y, float d_ref, double pix_thr, float rel_thr) {
+    PairResult r;
+    const double dr = (double)d_ref;
+    // step 1: reference pixel -> 3-D -> source pixel (:619-626)
+    double rx, ry, rz;
+    mat3_vec(c.Kri, (double)x * dr, (double)y * dr, dr, rx, ry, rz);
+    double sx, sy, sz;
+    mat3_vec(c.Rrel, rx, ry, rz, sx, sy, sz);
+    sx += c.trel[0]; sy += c.trel[1]; sz += c.trel[2];
+    double qx, qy, qz;
+    mat3_vec(c.Ks, sx, sy, sz, qx, qy, qz);
+    const double u = qx / qz, v = qy / qz;
+    r.x_src = (float)u;  // :630-631
+    r.y_src = (float)v;
+    // step 2: sample the source depth and project back (:632-647)
+    const float ds = remap_linear(depth_src, H, W, r.x_src, r.y_src);
+    const double dsd = (double)ds;
+    double bx, by, bz;
+    mat3_vec(c.Ksi, u * dsd, v * dsd, dsd, bx, by, bz);
+    double wx, wy, wz;
+    mat3_vec(c.Rback, bx, by, bz, wx, wy, wz);
+    wx += c.tback[0]; wy += c.tback[1]; wz += c.tback[2];
+    r.depth_reprojected = (float)wz;
+    double px, py, pz;
+    mat3_vec(c.Kr, wx, wy, wz, px, py, pz);
+    const float xr = (float)(px / pz), yr = (float)(py / pz);
+    // :661-667: dist is float64 (float32 maps minus int64 grids), the relative depth difference is float32
+    const double dx = (double)xr - (double)x, dy = (double)yr - (double)y;
+    const double dist = sqrt(dx * dx + dy * dy);
+    const float rel = fabsf(r.depth_reprojected - d_ref) / d_ref;
+    r.mask = (dist < pix_thr) && (rel < rel_thr);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) geo_check_pair_kernel(const float* __restrict__ depth_ref,
+                                                             const float* __restrict__ depth_src,
+                                                             const __grid_constant__ PairCam cam,
+                                                             double pix_thr, float rel_thr,
+                                                             uint8_t* __restrict__ mask,
+                                                             float* __restrict__ depth_rep, float* __restrict__ x2d,
+                                                             float* __restrict__ y2d, int H, int W) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    // the 560-byte camera block is a kernel parameter: it sits in the constant bank and is read with uniform loads
+    const size_t i = (size_t)y * W + x;
+    const PairResult r = check_pair(cam, depth_src, H, W, x, y, depth_ref[i], pix_thr, rel_thr);
+    mask[i] = r.mask ? 1 : 0;
+    depth_rep[i] = r.mask ? r.depth_reprojected : 0.0f;  // :668
+    x2d[i] = r.x_src;
+    y2d[i] = r.y_src;
+}
+
+struct GeoFilterParams {
+    const float* depths;
+    const float* confs;
+    const PairCam* cams;  // [R, S]
+    const int* refs;      // [R]
+    uint8_t* photo;
+    uint8_t* geo;
+    uint8_t* final_mask;
+    float* depth_avg;
+    int* geo_sum;
+    int S, H, W;
+    double pix_thr;
+    float rel_thr, photo_thr;
+    int geo_thr;
+};
+
+__global__ void __launch_bounds__(256) geo_filter_kernel(const GeoFilterParams p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int r = blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t i = (size_t)y * p.W + x;
+    const int ref = p.refs[r];
+    const float d_ref = p.depths[(size_t)ref * plane + i];
+    int votes = 0;
+    float sum = 0.0f;  // float32 running sum, like sum(list of float32 arrays) at :744
+    for (int s = 0; s < p.S; ++s) {
+        const PairCam& c = p.cams[(size_t)r * p.S + s];
+        if (c.src < 0) continue;
+        const PairResult pr = check_pair(c, p.depths + (size_t)c.src * plane, p.H, p.W, x, y, d_ref, p.pix_thr,
+                                         p.rel_thr);
+        votes += pr.mask ? 1 : 0;
+        sum = __fadd_rn(sum, pr.mask ? pr.depth_reprojected : 0.0f);
+    }
+    const size_t o = (size_t)r * plane + i;
+    const bool ph = p.confs[(size_t)ref * plane + i] > p.photo_thr;  // :716
+    const bool ge = votes >= p.geo_thr;                               // :746
+    p.photo[o] = ph;
+    p.geo[o] = ge;
+    p.final_mask[o] = ph && ge;                                       // :749
+    // :744 - float32 sum divided by an int32 count gives float64 in NumPy; rounded to float32 on output
+    p.depth_avg[o] = (float)((double)__fadd_rn(sum, d_ref) / (double)(votes + 1));
+    if (p.geo_sum != nullptr) p.geo_sum[o] = votes;
+}
+
+// ---- host: float64 camera algebra (the same products np.linalg.inv / np.matmul form in the reference) -------
+static void inv3(const double* m, double* o) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const double det = a * A + b * B + c * C;
+    const double id = 1.0 / det;
+    o[0] = A * id; o[1] = -(b * i - c * h) * id; o[2] = (b * f - c * e) * id;
+    o[3] = B * id; o[4] = (a * i - c * g) * id;  o[5] = -(a * f - c * d) * id;
+    o[6] = C * id; o[7] = -(a * h - b * g) * id; o[8] = (a * e - b * d) * id;
+}
+
+static void inv4(const double* m, double* out) {
+    double a[4][8];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) { a[i][j] = m[i * 4 + j]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r)
+            if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+        if (piv != c)
+            for (int j = 0; j < 8; ++j) { double t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+        const double d = 1.0 / a[c][c];
+        for (int j = 0; j < 8; ++j) a[c][j] *= d;
+        for (int r = 0; r < 4; ++r) {
+            if (r == c) continue;
+            const double f = a[r][c];
+            for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) out[i * 4 + j] = a[i][4 + j];
+}
+
+static void mul4(const double* a, const double* b, double* o) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            o[i * 4 + j] = s;
+        }
+}
+
+static void make_pair_cam(const double* Kr, const double* Er, const double* Ks, const double* Es, int src,
+                          PairCam* c) {
+    double Eri[16], Esi[16], rel[16], back[16];
+    inv4(Er, Eri);
+    inv4(Es, Esi);
+    mul4(Es, Eri, rel);    // :622
+    mul4(Er, Esi, back);   // :640
+    inv3(Kr, c->Kri);      // :619
+    inv3(Ks, c->Ksi);      // :637
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            c->Rrel[i * 3 + j] = rel[i * 4 + j];
+            c->Rback[i * 3 + j] = back[i * 4 + j];
+            c->Ks[i * 3 + j] = Ks[i * 3 + j];
+            c->Kr[i * 3 + j] = Kr[i * 3 + j];
+        }
+        c->trel[i] = rel[i * 4 + 3];
+        c->tback[i] = back[i * 4 + 3];
+    }
+    c->src = src;
+    c->pad = 0;
+}
+
+}  // namespace mvster
+
+using namespace mvster;
+
+extern "C" int mvster_geo_check_pair(const float* depth_ref, const double* K_ref, const double* E_ref,
+                                     const float* depth_src, const double* K_src, const double* E_src,
+                                     double condmask_pixel, double condmask_depth, uint8_t* mask,
+                                     float* depth_reprojected, float* x2d_src, float* y2d_src, int H, int W,
+                                     void* stream) {
+    if (!depth_ref || !K_ref || !E_ref || !depth_src || !K_src || !E_src || !mask || !depth_reprojected ||
+        !x2d_src || !y2d_src)
+        return fail(MVSTER_ERR_BAD_ARG, "geo_check_pair: null pointer");
+    if (H <= 0 || W <= 0) return fail(MVSTER_ERR_BAD_ARG, "geo_check_pair: non-positive dimension");
+    DeviceGuard guard(mask);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    PairCam cam;
+    make_pair_cam(K_ref, E_ref, K_src, E_src, 0, &cam);
+    dim3 grid((W + 31) / 32, (H + 7) / 8);
+    // NumPy compares the float64 pixel distance with a Python float (float64) and the float32 relative depth
+    // difference with the same scalar cast to float32
+    geo_check_pair_kernel<<<grid, 256, 0, s>>>(depth_ref, depth_src, cam, condmask_pixel, (float)condmask_depth, mask,
+                                               depth_reprojected, x2d_src, y2d_src, H, W);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("geo_check_pair launch");
+    return MVSTER_OK;
+}
+
+extern "C" int mvster_geo_filter(const float* depths, const float* confs, const double* K, const double* E,
+                                 const int32_t* pairs, int V, int R, int S, double condmask_pixel,
+                                 double condmask_depth, double photomask, int geomask, uint8_t* photo, uint8_t* geo,
+                                 uint8_t* final_mask, float* depth_avg, int32_t* geo_sum, int H, int W,
+                                 void* stream) {
+    if (!depths || !confs || !K || !E || !pairs || !photo || !geo || !final_mask || !depth_avg)
+        return fail(MVSTER_ERR_BAD_ARG, "geo_filter: null pointer");
+    if (V <= 0 || R <= 0 || S < 0 || H <= 0 || W <= 0) return fail(MVSTER_ERR_BAD_ARG, "geo_filter: bad dimension");
+    if (R > 65535) return fail(MVSTER_ERR_UNSUPPORTED, "geo_filter: more than 65535 reference views per call");
+    DeviceGuard guard(depth_avg);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int Sa = S > 0 ? S : 1;
+    std::vector<PairCam> cams((size_t)R * Sa);
+    std::vector<int> refs(R);
+    for (int r = 0; r < R; ++r) {
+        const int ref = pairs[(size_t)r * (1 + S)];
+        if (ref < 0 || ref >= V) return fail(MVSTER_ERR_BAD_ARG, "geo_filter: pairs[%d][0]=%d out of range", r, ref);
+        refs[r] = ref;
+        for (int j = 0; j < Sa; ++j) {
+            PairCam& c = cams[(size_t)r * Sa + j];
+            const int src = j < S ? pairs[(size_t)r * (1 + S) + 1 + j] : -1;
+            if (src >= V) return fail(MVSTER_ERR_BAD_ARG, "geo_filter: pairs[%d][%d]=%d out of range", r, j + 1, src);
+            if (src < 0) { c = PairCam{}; c.src = -1; continue; }
+            make_pair_cam(K + (size_t)ref * 9, E + (size_t)ref * 16, K + (size_t)src * 9, E + (size_t)src * 16, src, &c);
+        }
+    }
+    const size_t cam_bytes = cams.size() * sizeof(PairCam), ref_bytes = refs.size() * sizeof(int);
+    char* dev = nullptr;
+    cudaError_t e = cudaMallocAsync(&dev, cam_bytes + ref_bytes, s);
+    if (e != cudaSuccess) return check_cuda(e, "geo_filter: cudaMallocAsync");
+    e = cudaMemcpyAsync(dev, cams.data(), cam_bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dev + cam_bytes, refs.data(), ref_bytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { cudaFreeAsync(dev, s); return check_cuda(e, "geo_filter: H2D"); }
+    GeoFilterParams p{depths, confs, reinterpret_cast<const PairCam*>(dev), reinterpret_cast<const int*>(dev + cam_bytes),
+                      photo, geo, final_mask, depth_avg, geo_sum, Sa, H, W, condmask_pixel, (float)condmask_depth,
+                      (float)photomask, geomask};
+    dim3 grid((W + 31) / 32, (H + 7) / 8, R);
+    geo_filter_kernel<<<grid, 256, 0, s>>>(p);
+    count_launch();
+    cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(dev, s);
+    if (le != cudaSuccess) return check_cuda(le, "geo_filter launch");
+    return MVSTER_OK;
+}

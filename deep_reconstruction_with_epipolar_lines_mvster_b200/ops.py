@@ -1,0 +1,256 @@
+"""Thin torch-tensor front end of the C ABI: argument checking, output allocation, stream and pointer plumbing.
+
+PyTorch is used here only for device memory and streams; all arithmetic happens in libmvster_b200.so.
+Every function raises RuntimeError when the CUDA library is missing or a tensor is not on a CUDA device - there is
+no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+DEPTH_ARGMAX, DEPTH_REGRESS = 0, 1
+MAX_SRC_VIEWS = 15
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: the MVSTER B200 path has no CPU fallback" % name)
+
+
+def _stream(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError("features must be float32 or bfloat16, got %s" % t.dtype)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def to_nhwc(feat: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``[B,C,H,W]``-shaped tensor -> contiguous ``[B,H,W,C]`` tensor of ``dtype`` (default: keep).
+
+    Zero-copy when ``feat`` already has channels_last strides and the right dtype; NCHW-contiguous fp32 input goes
+    through the library's transpose(+cast) kernel (one pass).
+    """
+    _require_cuda(feat, "features")
+    if feat.dim() != 4:
+        raise RuntimeError("features must be [B,C,H,W], got %s" % (tuple(feat.shape),))
+    dtype = dtype or feat.dtype
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("feature dtype must be float32 or bfloat16")
+    nhwc_view = feat.permute(0, 2, 3, 1)
+    if nhwc_view.is_contiguous():
+        out = nhwc_view if feat.dtype == dtype else nhwc_view.to(dtype)
+    elif feat.dtype == torch.float32 and feat.is_contiguous():
+        b, c, h, w = feat.shape
+        out = torch.empty((b, h, w, c), device=feat.device, dtype=dtype)
+        lib = _lib.load()
+        _lib.check(lib.mvster_nchw_to_nhwc(_ptr(feat), _ptr(out), b, c, h, w, BF16 if dtype == torch.bfloat16 else F32,
+                                           _stream(feat)))
+    else:
+        out = nhwc_view.contiguous().to(dtype)
+    if out.data_ptr() % 32:
+        out = out.clone()
+    return out
+
+
+def compose_homographies(proj_matrices: torch.Tensor) -> torch.Tensor:
+    """``[B,N,2,4,4]`` -> ``rt [B,N-1,12]`` fp32 (reference mvs4net_utils.py:1047-1050 + :32-34)."""
+    proj = _f32c(proj_matrices, "proj_matrices")
+    if proj.dim() != 5 or tuple(proj.shape[2:]) != (2, 4, 4):
+        raise RuntimeError("proj_matrices must be [B,N,2,4,4], got %s" % (tuple(proj.shape),))
+    b, n = proj.shape[:2]
+    rt = torch.empty((b, n - 1, 12), device=proj.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_compose_homographies(_ptr(proj), _ptr(rt), b, n, _stream(proj)))
+    return rt
+
+
+def compose_homography_pair(src_proj: torch.Tensor, ref_proj: torch.Tensor) -> torch.Tensor:
+    sp, rp = _f32c(src_proj, "src_proj"), _f32c(ref_proj, "ref_proj")
+    b = sp.shape[0]
+    rt = torch.empty((b, 12), device=sp.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_compose_homography_pair(_ptr(sp), _ptr(rp), _ptr(rt), b, _stream(sp)))
+    return rt
+
+
+def epi_fwd(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch.Tensor, hypo: torch.Tensor,
+            groups: int, attn_temp: float, want_wsum: bool = False, want_weights: bool = False
+            ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Fused K1 forward on NHWC features.  Returns ``(volume [B,G,D,H,W], wsum or None, weights or None)``."""
+    _require_cuda(ref_nhwc, "ref")
+    b, h, w, c = ref_nhwc.shape
+    nsrc = len(srcs_nhwc)
+    hs, ws = srcs_nhwc[0].shape[1:3]
+    for s in srcs_nhwc:
+        if s.shape != srcs_nhwc[0].shape or s.shape[0] != b or s.shape[3] != c or s.dtype != ref_nhwc.dtype \
+                or not s.is_contiguous() or s.device != ref_nhwc.device:
+            raise RuntimeError("source features must share shape [B,Hs,Ws,C], dtype, device and be contiguous")
+    if not ref_nhwc.is_contiguous():
+        raise RuntimeError("ref features must be contiguous NHWC")
+    hypo = _f32c(hypo, "depth_hypo")
+    d = hypo.shape[1]
+    if tuple(hypo.shape) != (b, d, h, w):
+        raise RuntimeError("depth_hypo must be [B,D,H,W] = [%d,D,%d,%d], got %s" % (b, h, w, tuple(hypo.shape)))
+    if tuple(rt.shape) != (b, nsrc, 12) or rt.dtype != torch.float32 or not rt.is_contiguous():
+        raise RuntimeError("rt must be contiguous fp32 [B,Nsrc,12]")
+    dev = ref_nhwc.device
+    out = torch.empty((b, groups, d, h, w), device=dev, dtype=torch.float32)
+    wsum = torch.empty((b, d, h, w), device=dev, dtype=torch.float32) if want_wsum else None
+    weights = torch.empty((b, nsrc, d, h, w), device=dev, dtype=torch.float32) if want_weights else None
+    _lib.check(_lib.load().mvster_epi_fwd(
+        _ptr(ref_nhwc), _ptr_array(srcs_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), _ptr(wsum), _ptr(weights),
+        b, nsrc, c, groups, d, h, w, hs, ws, float(attn_temp), _dtype_code(ref_nhwc), _stream(ref_nhwc)))
+    return out, wsum, weights
+
+
+def epi_bwd(ref_nhwc, srcs_nhwc, rt, hypo, out, wsum, gout, groups: int, attn_temp: float
+            ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """K1 backward.  Returns ``(grad_ref [B,H,W,C] fp32, [grad_src_v [B,Hs,Ws,C] fp32])``."""
+    b, h, w, c = ref_nhwc.shape
+    nsrc = len(srcs_nhwc)
+    hs, ws = srcs_nhwc[0].shape[1:3]
+    d = hypo.shape[1]
+    gout = _f32c(gout, "grad_output")
+    dev = ref_nhwc.device
+    grad_ref = torch.empty((b, h, w, c), device=dev, dtype=torch.float32)
+    grad_all = torch.zeros((nsrc, b, hs, ws, c), device=dev, dtype=torch.float32)  # one memset for all views
+    grad_srcs = [grad_all[v] for v in range(nsrc)]
+    _lib.check(_lib.load().mvster_epi_bwd(
+        _ptr(ref_nhwc), _ptr_array(srcs_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), _ptr(wsum), _ptr(gout),
+        _ptr(grad_ref), _ptr_array(grad_srcs), b, nsrc, c, groups, d, h, w, hs, ws, float(attn_temp),
+        _dtype_code(ref_nhwc), _stream(ref_nhwc)))
+    return grad_ref, grad_srcs
+
+
+def homo_warp(src_nhwc: torch.Tensor, rt: torch.Tensor, hypo: torch.Tensor) -> torch.Tensor:
+    b, hs, ws, c = src_nhwc.shape
+    hypo = _f32c(hypo, "depth_values")
+    _, d, h, w = hypo.shape
+    out = torch.empty((b, c, d, h, w), device=src_nhwc.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_homo_warp(_ptr(src_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), b, c, d, h, w, hs, ws,
+                                            _dtype_code(src_nhwc), _stream(src_nhwc)))
+    return out
+
+
+def init_inverse_range(depth_values: torch.Tensor, ndepths: int, h: int, w: int) -> torch.Tensor:
+    dv = _f32c(depth_values, "depth_values")
+    b, nv = dv.shape
+    hypo = torch.empty((b, ndepths, h, w), device=dv.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_init_inverse_range(_ptr(dv), nv, _ptr(hypo), b, ndepths, h, w, _stream(dv)))
+    return hypo
+
+
+def schedule_inverse_range(inv_min: torch.Tensor, inv_max: torch.Tensor, ndepths: int, h: int, w: int) -> torch.Tensor:
+    lo, hi = _f32c(inv_min, "inverse_min_depth"), _f32c(inv_max, "inverse_max_depth")
+    b = lo.shape[0]
+    if tuple(lo.shape) != (b, h // 2, w // 2) or lo.shape != hi.shape:
+        raise RuntimeError("inverse_min/max_depth must be [B,H//2,W//2] = [%d,%d,%d], got %s / %s"
+                           % (b, h // 2, w // 2, tuple(lo.shape), tuple(hi.shape)))
+    hypo = torch.empty((b, ndepths, h, w), device=lo.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_schedule_inverse_range(_ptr(lo), _ptr(hi), _ptr(hypo), b, ndepths, h, w, _stream(lo)))
+    return hypo
+
+
+def tail(logits: torch.Tensor, hypo: torch.Tensor, split_itv: float, want_conf: bool, inverse_depth: bool,
+         depth_mode: int = DEPTH_ARGMAX):
+    """K2a.  Returns ``(attn [B,D,H,W], depth [B,H,W], conf or None, inv_min or None, inv_max or None)``."""
+    lg, hy = _f32c(logits, "logits"), _f32c(hypo, "depth_hypo")
+    if lg.shape != hy.shape or lg.dim() != 4:
+        raise RuntimeError("logits and depth_hypo must both be [B,D,H,W], got %s / %s" % (tuple(lg.shape), tuple(hy.shape)))
+    b, d, h, w = lg.shape
+    dev = lg.device
+    attn = torch.empty_like(lg)
+    depth = torch.empty((b, h, w), device=dev, dtype=torch.float32)
+    conf = torch.empty((b, h, w), device=dev, dtype=torch.float32) if want_conf else None
+    inv_min = torch.empty((b, h, w), device=dev, dtype=torch.float32) if inverse_depth else None
+    inv_max = torch.empty((b, h, w), device=dev, dtype=torch.float32) if inverse_depth else None
+    _lib.check(_lib.load().mvster_tail(_ptr(lg), _ptr(hy), float(split_itv), int(depth_mode), _ptr(attn), _ptr(depth),
+                                       _ptr(conf), _ptr(inv_min), _ptr(inv_max), b, d, h, w, _stream(lg)))
+    return attn, depth, conf, inv_min, inv_max
+
+
+def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:
+    b, d, h, w = attn.shape
+    g_attn = None if g_attn is None else _f32c(g_attn, "grad attn")
+    g_depth = None if g_depth is None else _f32c(g_depth, "grad depth")
+    g_logits = torch.empty_like(attn)
+    _lib.check(_lib.load().mvster_tail_bwd(_ptr(attn), _ptr(hypo), _ptr(depth), _ptr(g_attn), _ptr(g_depth),
+                                           int(depth_mode), _ptr(g_logits), b, d, h, w, _stream(attn)))
+    return g_logits
+
+
+def _dbl(a, n) -> "ctypes.Array":
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    if arr.size != n:
+        raise RuntimeError("expected %d camera values, got %d" % (n, arr.size))
+    return arr
+
+
+def geo_check_pair(depth_ref: torch.Tensor, k_ref, e_ref, depth_src: torch.Tensor, k_src, e_src,
+                   condmask_pixel: float, condmask_depth: float):
+    dr, ds = _f32c(depth_ref, "depth_ref"), _f32c(depth_src, "depth_src")
+    h, w = dr.shape
+    if ds.shape != dr.shape:
+        raise RuntimeError("depth_ref and depth_src must have the same [H,W] shape")
+    dev = dr.device
+    mask = torch.empty((h, w), device=dev, dtype=torch.uint8)
+    drep = torch.empty((h, w), device=dev, dtype=torch.float32)
+    x2d = torch.empty_like(drep)
+    y2d = torch.empty_like(drep)
+    dp = ctypes.POINTER(ctypes.c_double)
+    kr, er, ks, es = _dbl(k_ref, 9), _dbl(e_ref, 16), _dbl(k_src, 9), _dbl(e_src, 16)
+    _lib.check(_lib.load().mvster_geo_check_pair(
+        _ptr(dr), kr.ctypes.data_as(dp), er.ctypes.data_as(dp), _ptr(ds), ks.ctypes.data_as(dp), es.ctypes.data_as(dp),
+        float(condmask_pixel), float(condmask_depth), _ptr(mask), _ptr(drep), _ptr(x2d), _ptr(y2d), h, w, _stream(dr)))
+    return mask.bool(), drep, x2d, y2d
+
+
+def geo_filter(depths: torch.Tensor, confs: torch.Tensor, ks, es, pairs, condmask_pixel: float, condmask_depth: float,
+               photomask: float, geomask: int, want_geo_sum: bool = False):
+    """K2b over a whole scene.  ``pairs`` [R, 1+S] int (ref, sources...; negative source = skip)."""
+    dz, cf = _f32c(depths, "depths"), _f32c(confs, "confs")
+    v, h, w = dz.shape
+    pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32))
+    r, s1 = pr.shape
+    dev = dz.device
+    photo = torch.empty((r, h, w), device=dev, dtype=torch.uint8)
+    geo = torch.empty_like(photo)
+    final = torch.empty_like(photo)
+    avg = torch.empty((r, h, w), device=dev, dtype=torch.float32)
+    gsum = torch.empty((r, h, w), device=dev, dtype=torch.int32) if want_geo_sum else None
+    kk, ee = _dbl(ks, v * 9), _dbl(es, v * 16)
+    dp = ctypes.POINTER(ctypes.c_double)
+    _lib.check(_lib.load().mvster_geo_filter(
+        _ptr(dz), _ptr(cf), kk.ctypes.data_as(dp), ee.ctypes.data_as(dp),
+        pr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), v, r, s1 - 1, float(condmask_pixel), float(condmask_depth),
+        float(photomask), int(geomask), _ptr(photo), _ptr(geo), _ptr(final), _ptr(avg), _ptr(gsum), h, w, _stream(dz)))
+    return photo.bool(), geo.bool(), final.bool(), avg, gsum

@@ -1,0 +1,149 @@
+/*
+ * mvster_b200.h - C ABI of the B200-native MVSTER cost-volume hot path (libmvster_b200.so).
+ *
+ * The reference (olivier-2018/Deep_reconstruction_with_epipolar_lines_MVSTER) is pure Python/PyTorch and has no
+ * FFI of its own; its seam for this path is a set of Python call signatures.  Every entry point below names the
+ * reference interface (file:line, relative to the reference tree) it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all sizes are ints, all buffers are raw pointers.
+ *   - "dev" pointers are CUDA device pointers owned by the caller; kernels never allocate or free them.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Launches are asynchronous;
+ *     a launch-time failure is returned immediately, an execution fault surfaces at the caller's next sync.
+ *   - every function returns MVSTER_OK (0) or an mvster_status; mvster_last_error() returns a thread-local
+ *     human-readable message for the last non-zero status on the calling thread.
+ *   - the device is taken from the output pointer (cudaPointerGetAttributes) and restored on return, so the
+ *     library is safe under nn.DataParallel (one host thread per GPU, reference test_mvs4.py:393).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns MVSTER_ERR_NO_DEVICE.
+ *
+ * Feature layout: NHWC ("channels_last"), i.e. [B, H, W, C] with C contiguous; fp32 or bf16.
+ */
+#ifndef MVSTER_B200_H
+#define MVSTER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSTER_ABI_VERSION 1
+#define MVSTER_MAX_SRC_VIEWS 15 /* source views per launch (reference NviewGen <= 16) */
+
+typedef enum mvster_status {
+    MVSTER_OK = 0,
+    MVSTER_ERR_BAD_ARG = 1,     /* null pointer, non-positive size, ...                         */
+    MVSTER_ERR_UNSUPPORTED = 2, /* (C, G, D) combination or mode without a compiled kernel       */
+    MVSTER_ERR_ALIGN = 3,       /* a feature pointer is not 32-byte (fp32) / 16-byte (bf16) aligned */
+    MVSTER_ERR_CUDA = 4,        /* a CUDA runtime call failed; message holds cudaGetErrorString  */
+    MVSTER_ERR_NO_DEVICE = 5    /* no usable CUDA device / pointer is not device memory          */
+} mvster_status;
+
+typedef enum mvster_dtype { MVSTER_F32 = 0, MVSTER_BF16 = 1 } mvster_dtype;
+
+typedef enum mvster_depth_mode {
+    MVSTER_DEPTH_ARGMAX = 0, /* reference default: models/mvs4net_utils.py:1129-1130               */
+    MVSTER_DEPTH_REGRESS = 1 /* depth_regression, models/module.py:935-941 (= commented :1133)     */
+} mvster_depth_mode;
+
+int mvster_version(void);
+const char* mvster_last_error(void);
+/* number of kernel launches issued by this library on the calling process since load (for bench accounting) */
+uint64_t mvster_launch_count(void);
+
+/* ---- K0: relative homographies ---------------------------------------------------------------------------
+ * Replaces the per-view prologue of stagenet.forward (models/mvs4net_utils.py:1047-1050: P = E with rows 0..2 :=
+ * K[:3,:3] @ E[:3,:4]) and homo_warping's `proj = src_proj @ inverse(ref_proj)` (:32-34), done once per stage for
+ * all views in float64 on the device (no host sync).
+ *   proj  dev [B, N, 2, 4, 4] fp32   ([:, v, 0] = extrinsic 4x4, [:, v, 1, :3, :3] = intrinsic)
+ *   rt    dev [B, N-1, 12]    fp32   row-major 3x4 [R | t] of M_v = P_v @ inv(P_0), v = 1..N-1
+ */
+int mvster_compose_homographies(const float* proj, float* rt, int B, int N, void* stream);
+/* same from already-composed 4x4 projections (the arguments of homo_warping, :21): src_proj, ref_proj dev [B,4,4] */
+int mvster_compose_homography_pair(const float* src_proj, const float* ref_proj, float* rt, int B, void* stream);
+
+/* ---- K1 forward: fused homography warp + group correlation + epipolar attention + view aggregation ---------
+ * Replaces stagenet.forward steps 1-2 (models/mvs4net_utils.py:1030-1102) including homo_warping (:21-67); the
+ * [B,C,D,H,W] warped volume is never materialised.
+ *   ref      dev [B, H, W, C]      reference-view features, `dtype`
+ *   src      HOST array of Nsrc dev pointers, each [B, Hs, Ws, C], `dtype`
+ *   rt       dev [B, Nsrc, 12]     from mvster_compose_homographies
+ *   hypo     dev [B, D, H, W]      depth hypotheses, fp32
+ *   out      dev [B, G, D, H, W]   aggregated correlation volume (regnet input), fp32, written in full
+ *   wsum     dev [B, D, H, W]      optional (NULL ok): 1e-8 + sum_v w_v, needed by the backward
+ *   weights  dev [B, Nsrc, D, H, W] optional (NULL ok): per-view attention weights (reference `cor_weight`, :1083)
+ * Supported: C in {8,16,32,64}, C/G in {1,2,4,8}, D in {4,8}; group_cor=True, attn_fuse_d=True (every shipped config).
+ */
+int mvster_epi_fwd(const void* ref, const void* const* src, const float* rt, const float* hypo, float* out,
+                   float* wsum, float* weights, int B, int Nsrc, int C, int G, int D, int H, int W, int Hs, int Ws,
+                   float attn_temp, int dtype, void* stream);
+
+/* ---- K1 backward -----------------------------------------------------------------------------------------
+ * Replaces autograd through the same lines (grid_sampler_2d_backward, softmax_backward, ...).  Gradients flow to
+ * the reference and source features only (the sampling grid is built under no_grad, :31; depth_hypo is detached at
+ * models/MVS4Net.py:116).
+ *   out, wsum  dev  the forward's outputs (saved; nothing else is stored between forward and backward)
+ *   gout       dev [B, G, D, H, W] fp32
+ *   grad_ref   dev [B, H, W, C]   fp32, written in full
+ *   grad_src   HOST array of Nsrc dev pointers, each [B, Hs, Ws, C] fp32, ACCUMULATED with atomics: the caller
+ *              zero-initialises them
+ */
+int mvster_epi_bwd(const void* ref, const void* const* src, const float* rt, const float* hypo, const float* out,
+                   const float* wsum, const float* gout, float* grad_ref, float* const* grad_src, int B, int Nsrc,
+                   int C, int G, int D, int H, int W, int Hs, int Ws, float attn_temp, int dtype, void* stream);
+
+/* ---- homo_warping compatibility (models/mvs4net_utils.py:21-67): materialises [B, C, D, H, W] fp32 -------- */
+int mvster_homo_warp(const void* src, const float* rt /* dev [B,12] */, const float* hypo, float* warped, int B,
+                     int C, int D, int H, int W, int Hs, int Ws, int dtype, void* stream);
+
+/* ---- hypothesis schedule (models/mvs4net_utils.py:79-85 and :87-94) --------------------------------------
+ *   depth_values dev [B, nvals] fp32 (only [:,0] and [:,nvals-1] are used, as in the reference)
+ *   inv_min/max  dev [B, H/2, W/2] fp32  (previous stage's inverse_min_depth / inverse_max_depth)
+ *   hypo         dev [B, D, H, W] fp32
+ */
+int mvster_init_inverse_range(const float* depth_values, int nvals, float* hypo, int B, int D, int H, int W,
+                              void* stream);
+int mvster_schedule_inverse_range(const float* inv_min, const float* inv_max, float* hypo, int B, int D, int H,
+                                  int W, void* stream);
+
+/* ---- K2a: depth / confidence tail (models/mvs4net_utils.py:1109-1156) --------------------------------------
+ *   logits dev [B, D, H, W] regnet output;  hypo dev [B, D, H, W]
+ *   attn   dev [B, D, H, W] softmax_D(logits)                           (ret_dict["attn_weight"])
+ *   depth  dev [B, H, W]    hypo[argmax attn] or sum attn*hypo            (ret_dict["depth"])
+ *   conf   dev [B, H, W]    max_D logits / sum_D logits; NULL in training (ret_dict["photometric_confidence"])
+ *   inv_min / inv_max dev [B, H, W]: 1/depth +- split_itv * (1/hypo[:,2] - 1/hypo[:,1]); NULL when !inverse_depth
+ */
+int mvster_tail(const float* logits, const float* hypo, float split_itv, int depth_mode, float* attn, float* depth,
+                float* conf, float* inv_min, float* inv_max, int B, int D, int H, int W, void* stream);
+/* backward of the tail w.r.t. the logits: softmax backward of g_attn (+ the regression term of g_depth when
+ * depth_mode == MVSTER_DEPTH_REGRESS); g_attn / g_depth may be NULL (treated as zero) */
+int mvster_tail_bwd(const float* attn, const float* hypo, const float* depth, const float* g_attn,
+                    const float* g_depth, int depth_mode, float* g_logits, int B, int D, int H, int W, void* stream);
+
+/* ---- K2b: geometric consistency filter (test_mvs4.py:612-670) and mask fusion (:716-749) ------------------
+ * mvster_geo_check_pair == check_geometric_consistency for one (ref, src) pair:
+ *   depth_ref, depth_src dev [H, W] fp32; K_* HOST 3x3 double; E_* HOST 4x4 double (as read by
+ *   read_camera_parameters, test_mvs4.py:143-151)
+ *   mask dev [H, W] uint8; depth_reprojected, x2d_src, y2d_src dev [H, W] fp32
+ * mvster_geo_filter fuses all S source views of R reference views in one launch:
+ *   depths, confs dev [V, H, W] fp32; K HOST [V, 9] double; E HOST [V, 16] double
+ *   pairs HOST [R, 1+S] int32: (ref view, S source views); a negative source id is skipped
+ *   photo, geo, final dev [R, H, W] uint8; depth_avg dev [R, H, W] fp32; geo_sum dev [R, H, W] int32 (NULL ok)
+ */
+int mvster_geo_check_pair(const float* depth_ref, const double* K_ref, const double* E_ref, const float* depth_src,
+                          const double* K_src, const double* E_src, double condmask_pixel, double condmask_depth,
+                          uint8_t* mask, float* depth_reprojected, float* x2d_src, float* y2d_src, int H, int W,
+                          void* stream);
+int mvster_geo_filter(const float* depths, const float* confs, const double* K, const double* E, const int32_t* pairs,
+                      int V, int R, int S, double condmask_pixel, double condmask_depth, double photomask, int geomask,
+                      uint8_t* photo, uint8_t* geo, uint8_t* final_mask, float* depth_avg, int32_t* geo_sum, int H,
+                      int W, void* stream);
+
+/* ---- layout helper: NCHW fp32 -> NHWC fp32/bf16 (the FPN emits NCHW, models/mvs4net_utils.py:504-507) ----- */
+int mvster_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSTER_B200_H */

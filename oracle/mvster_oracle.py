@@ -63,15 +63,18 @@ def relative_homography_np(proj: np.ndarray) -> np.ndarray:
 # K1: homography warp + group correlation + epipolar attention + view aggregation
 #                                                                             models/mvs4net_utils.py:21-67,1027-1102
 # ---------------------------------------------------------------------------------------------------------------
-def sample_coords_np(rt: np.ndarray, hypo: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+def sample_coords_np(rt: np.ndarray, hypo: np.ndarray, origin: Tuple[int, int] = (0, 0)
+                     ) -> Tuple[np.ndarray, np.ndarray]:
     """Source-image sample coordinates for every (pixel, hypothesis).
 
-    ``rt`` [3,4] float64, ``hypo`` [D,H,W] -> (sx, sy) each [D,H,W] float64.
+    ``rt`` [3,4] float64, ``hypo`` [D,H,W] -> (sx, sy) each [D,H,W] float64.  ``origin`` = (y0, x0) of ``hypo``'s
+    top-left pixel in the full reference image (for checking a window of a large image).
     models/mvs4net_utils.py:36-48: p = R @ [x, y, 1]^T * d + t ; z == 0 -> 1e-9 ; (sx, sy) = p.xy / z.
     The normalise (:51-52) / un-normalise (grid_sample, align_corners=True) pair is the identity in exact math.
     """
     d, h, w = hypo.shape
-    ys, xs = np.meshgrid(np.arange(h, dtype=np.float64), np.arange(w, dtype=np.float64), indexing="ij")
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float64) + origin[0], np.arange(w, dtype=np.float64) + origin[1],
+                         indexing="ij")
     r = rt[:, :3]
     t = rt[:, 3]
     ax = r[0, 0] * xs + r[0, 1] * ys + r[0, 2]
@@ -129,13 +132,21 @@ def homo_warping_np(src_fea: np.ndarray, src_proj: np.ndarray, ref_proj: np.ndar
 
 def epipolar_aggregate_np(ref: np.ndarray, srcs: Sequence[np.ndarray], proj: np.ndarray, hypo: np.ndarray,
                           groups: int, attn_temp: float, group_cor: bool = True, attn_fuse_d: bool = True,
-                          rt: Optional[np.ndarray] = None):
+                          rt: Optional[np.ndarray] = None, window: Optional[Tuple[int, int, int, int]] = None):
     """Float64 restatement of ``stagenet.forward`` steps 1-2 (models/mvs4net_utils.py:1030-1102).
 
     ``ref`` [B,C,H,W]; ``srcs`` list of N-1 arrays [B,C,Hs,Ws]; ``proj`` [B,N,2,4,4]; ``hypo`` [B,D,H,W].
     Returns ``(volume [B,G,D,H,W], weights [B,N-1,D,H,W] (or [B,N-1,H,W] when not attn_fuse_d), wsum)``.
     ``rt`` overrides the homographies (e.g. the fp32-rounded ones the CUDA path uses).
+    ``window`` = (y0, y1, x0, x1) restricts the computation to that block of reference pixels (the sources stay
+    whole), so that windows of full-size images can be checked in seconds.
     """
+    origin = (0, 0)
+    if window is not None:
+        y0, y1, x0, x1 = window
+        ref = ref[:, :, y0:y1, x0:x1]
+        hypo = hypo[:, :, y0:y1, x0:x1]
+        origin = (y0, x0)
     b, c, h, w = ref.shape
     d = hypo.shape[1]
     if rt is None:
@@ -151,7 +162,7 @@ def epipolar_aggregate_np(ref: np.ndarray, srcs: Sequence[np.ndarray], proj: np.
         weights = np.zeros((b, len(srcs), h, w))
     for i in range(b):
         for v, src in enumerate(srcs):
-            sx, sy = sample_coords_np(rt[i, v], hypo[i])
+            sx, sy = sample_coords_np(np.asarray(rt[i, v], np.float64).reshape(3, 4), hypo[i], origin)
             warped = bilinear_zeros_np(src[i], sx, sy)                                       # [C,D,H,W]
             if group_cor:                                                                    # :1066-1069
                 cor = (warped.reshape(g, c // g, d, h, w) * ref64[i].reshape(g, c // g, 1, h, w)).mean(1)
@@ -438,3 +449,42 @@ def filter_fuse_np(depths: np.ndarray, confs: np.ndarray, ks: np.ndarray, es: np
         geo[i] = cnt >= geomask                                                                # :746
         final[i] = np.logical_and(photo[i], geo[i])                                            # :749
     return photo, geo, final, avg, gsum
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole hot path of one depth map on the CPU (what bench.py times as the CPU baseline / reference arm)
+# ---------------------------------------------------------------------------------------------------------------
+def cascade_port(features, projs, depth_values, logits, groups, ndepths, split_itv, attn_temp=2.0):
+    """The hot-path slice of ``MVS4net.forward`` (models/MVS4Net.py:99-136) on the CPU with the reference's own
+    op sequence: per stage the hypothesis schedule (:109-118), ``stagenet`` steps 1-2 (fp32 torch port above) and the
+    tail (:1109-1156, torch ops as in the reference).  ``regnet`` is out of scope: ``logits[s]`` stands in for its
+    output, exactly as in the GPU benchmark.
+
+    ``features[s]`` = list of N tensors [B,C,H,W]; ``projs[s]`` [B,N,2,4,4]; ``depth_values`` [B,2].
+    Returns the last stage's (depth, confidence).
+    """
+    out = None
+    for s in range(len(features)):
+        b, c, h, w = features[s][0].shape
+        d = ndepths[s]
+        if s == 0:                                                                          # MVS4Net.py:109-111
+            inv_min = 1.0 / depth_values[:, 0]
+            inv_max = 1.0 / depth_values[:, -1]
+            itv = torch.arange(0, d, dtype=torch.float32).reshape(1, -1, 1, 1).repeat(1, 1, h, w) / (d - 1)
+            hypo = 1.0 / (inv_max[:, None, None, None] + (inv_min - inv_max)[:, None, None, None] * itv)
+        else:                                                                               # MVS4Net.py:115-116
+            itv = torch.arange(0, d, dtype=torch.float32).reshape(1, -1, 1, 1).repeat(1, 1, h // 2, w // 2) / (d - 1)
+            inv = out["inverse_max_depth"][:, None] + (out["inverse_min_depth"] - out["inverse_max_depth"])[:, None] * itv
+            inv = F.interpolate(inv.unsqueeze(1), [d, h, w], mode="trilinear", align_corners=True).squeeze(1)
+            hypo = 1.0 / inv
+        vol = epipolar_aggregate_port(features[s], projs[s], hypo, groups[s], attn_temp)
+        lg = logits[s]
+        idx = lg.max(1, keepdim=True)[1]                                                    # :1109-1113
+        conf = torch.gather(lg, 1, idx).squeeze(1) / lg.sum(1)
+        attn = F.softmax(lg, dim=1)                                                         # :1126
+        depth = torch.gather(hypo, 1, attn.max(1, keepdim=True)[1]).squeeze(1)              # :1129-1130
+        last_itv = 1.0 / hypo[:, 2] - 1.0 / hypo[:, 1]                                      # :1152
+        out = {"depth": depth, "photometric_confidence": conf, "attn_weight": attn, "volume": vol,
+               "inverse_min_depth": 1 / depth + split_itv[s] * last_itv,
+               "inverse_max_depth": 1 / depth - split_itv[s] * last_itv}
+    return out["depth"], out["photometric_confidence"]

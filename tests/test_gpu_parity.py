@@ -1,0 +1,349 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libmvster_b200.so) against the golden vectors produced by
+the unmodified reference and against the CPU oracle on seeded inputs.  Run on a B200 with ``-m gpu``.
+
+Tolerances (BASELINE.json north_star): attention weights within 1e-4 and volume within 1e-4 for fp32 features
+(measured: ~1e-5, the reference's own fp32 noise floor); depth within 1e-3 of the depth interval wherever the
+arg-max agrees; filter masks identical on >= 99.99 % of pixels.  bf16 features: 2e-2 against the fp32 reference
+(stated looser bound: bf16 keeps 8 mantissa bits) and 1e-4 against exact math on the same bf16-rounded features.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import deep_reconstruction_with_epipolar_lines_mvster_b200 as mv
+from deep_reconstruction_with_epipolar_lines_mvster_b200 import ops, synthetic as syn
+from oracle import mvster_oracle as O
+
+DEV = "cuda"
+K1_CASES = ["k1_stage1", "k1_stage2", "k1_stage3", "k1_stage4", "k1_oob"]
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _features(g, channels_last=False, requires_grad=False):
+    feats = [_cuda(g["ref"])] + [_cuda(g["srcs"][:, v]) for v in range(g["srcs"].shape[1])]
+    if channels_last:
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    if requires_grad:
+        feats = [f.requires_grad_(True) for f in feats]
+    return feats
+
+
+# --------------------------------------------------------------------------------------------------------------
+# K1 forward / backward against the reference's golden vectors
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("name", K1_CASES)
+def test_k1_forward_matches_reference(golden, name, channels_last):
+    g = golden(name)
+    feats = _features(g, channels_last)
+    vol, wts = mv.epipolar_weights(feats, _cuda(g["proj"]), _cuda(g["hypo"]), int(g["groups"]), float(g["attn_temp"]))
+    assert vol.shape == g["volume"].shape and vol.dtype == torch.float32
+    assert np.abs(vol.cpu().numpy() - g["volume"]).max() < 1e-4
+    assert np.abs(wts.cpu().numpy() - g["weights"]).max() < 1e-4
+    vol2 = mv.epipolar_aggregate(feats, _cuda(g["proj"]), _cuda(g["hypo"]), int(g["groups"]), float(g["attn_temp"]))
+    assert torch.equal(vol, vol2)
+
+
+@pytest.mark.parametrize("name", K1_CASES)
+def test_k1_backward_matches_reference_autograd(golden, name):
+    g = golden(name)
+    feats = _features(g, requires_grad=True)
+    vol = mv.epipolar_aggregate(feats, _cuda(g["proj"]), _cuda(g["hypo"]), int(g["groups"]), float(g["attn_temp"]))
+    (vol * _cuda(g["gout"])).sum().backward()
+    gr = feats[0].grad.cpu().numpy()
+    scale = max(1.0, np.abs(g["grad_ref"]).max())
+    assert np.abs(gr - g["grad_ref"]).max() < 2e-4 * scale
+    for v in range(g["srcs"].shape[1]):
+        gs = feats[1 + v].grad.cpu().numpy()
+        scale = max(1.0, np.abs(g["grad_srcs"][:, v]).max())
+        assert np.abs(gs - g["grad_srcs"][:, v]).max() < 2e-4 * scale, (name, v)
+
+
+def test_k1_backward_is_reproducible_within_atomic_tolerance(golden):
+    g = golden("k1_stage4")
+    grads = []
+    for _ in range(2):
+        feats = _features(g, requires_grad=True)
+        vol = mv.epipolar_aggregate(feats, _cuda(g["proj"]), _cuda(g["hypo"]), int(g["groups"]), float(g["attn_temp"]))
+        (vol * _cuda(g["gout"])).sum().backward()
+        grads.append([f.grad.clone() for f in feats])
+    assert torch.equal(grads[0][0], grads[1][0])          # grad_ref: no atomics, bit-exact
+    for a, b in zip(grads[0][1:], grads[1][1:]):            # grad_src: fp32 atomics, order-dependent rounding only
+        assert (a - b).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["k1_stage2", "k1_stage4"])
+def test_k1_bf16_features(golden, name):
+    g = golden(name)
+    feats = _features(g)
+    proj, hypo = _cuda(g["proj"]), _cuda(g["hypo"])
+    vol = mv.epipolar_aggregate(feats, proj, hypo, int(g["groups"]), float(g["attn_temp"]),
+                                feature_dtype=torch.bfloat16).cpu().numpy()
+    # looser stated bound against the fp32 reference
+    assert np.abs(vol - g["volume"]).max() < 2e-2
+    # tight bound against exact math on the same bf16-rounded features
+    rnd = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    srcs = [rnd(g["srcs"][:, v]) for v in range(g["srcs"].shape[1])]
+    ref64, _, _ = O.epipolar_aggregate_np(rnd(g["ref"]), srcs, g["proj"], g["hypo"], int(g["groups"]),
+                                          float(g["attn_temp"]))
+    assert np.abs(vol - ref64).max() < 1e-4
+    # bf16 tensors passed directly take the same path
+    vol_b = mv.epipolar_aggregate([f.bfloat16() for f in feats], proj, hypo, int(g["groups"]),
+                                  float(g["attn_temp"])).cpu().numpy()
+    assert np.array_equal(vol, vol_b)
+
+
+def test_k1_all_samples_out_of_frame_gives_zero_volume():
+    b, c, g, d, h, w = 1, 8, 4, 4, 9, 11
+    feats = [syn.smooth_features(b, c, h, w, s, device=DEV) for s in range(3)]
+    proj = syn.proj_matrices(b, 3, h, w, 3)
+    proj[:, 1:, 0, 0, 3] += 1e5      # push the source cameras far away: every sample leaves the image
+    hypo = mv.init_inverse_range(_cuda(syn.depth_values(b)), d, None, None, h, w)
+    vol = mv.epipolar_aggregate(feats, _cuda(proj), hypo, g, 2.0)
+    assert torch.count_nonzero(vol).item() == 0
+
+
+def test_k1_identity_homography_known_answer():
+    """src camera == ref camera and src features == ref features: warped == ref exactly, every hypothesis scores the
+    same, softmax is uniform, and the volume is mean_c(ref^2) per group (times S/(S+1e-8))."""
+    b, c, g, d, h, w = 2, 16, 4, 4, 13, 37
+    ref = syn.smooth_features(b, c, h, w, 3, device=DEV)
+    proj = syn.proj_matrices(b, 3, h, w, 3)
+    proj[:, 1:] = proj[:, :1]
+    hypo = mv.init_inverse_range(_cuda(syn.depth_values(b)), d, None, None, h, w)
+    vol = mv.epipolar_aggregate([ref, ref.clone(), ref.clone()], _cuda(proj), hypo, g, 2.0)
+    expect = (ref.double() ** 2).reshape(b, g, c // g, h, w).mean(2)[:, :, None].expand(-1, -1, d, -1, -1)
+    # the identity is exact only up to the fp32 rounding of R = P P^-1 (sub-1e-3 px), hence a small tolerance
+    assert (vol.double() - expect).abs().max().item() < 2e-3
+    assert (vol[:, :, 0] - vol[:, :, 1]).abs().max().item() < 2e-3
+
+
+def test_k1_rejects_unsupported_configs(golden):
+    g = golden("k1_stage4")
+    feats = _features(g)
+    proj, hypo = _cuda(g["proj"]), _cuda(g["hypo"])
+    net = mv.stagenet(inverse_depth=True, attn_temp=2.0)
+    with pytest.raises(NotImplementedError):
+        net(feats, proj, hypo, lambda x: x.sum(1), 3, group_cor=False)
+    with pytest.raises(NotImplementedError):
+        mv.stagenet(inverse_depth=True, attn_fuse_d=False)(feats, proj, hypo, lambda x: x.sum(1), 3, group_cor=True,
+                                                           group_cor_dim=4)
+    with pytest.raises(RuntimeError, match="not in"):
+        bad = [torch.zeros(1, 24, 8, 8, device=DEV) for _ in range(2)]
+        mv.epipolar_aggregate(bad, proj[:, :2], torch.ones(1, 4, 8, 8, device=DEV), 4, 2.0)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        mv.epipolar_aggregate([f.cpu() for f in feats], proj.cpu(), hypo.cpu(), 4, 2.0)
+
+
+@pytest.mark.parametrize("stage,h0,w0,n", [(0, 256, 320, 5), (1, 128, 160, 4), (2, 128, 160, 5), (3, 96, 120, 5)])
+def test_k1_vs_oracle_seeded(stage, h0, w0, n):
+    """Moderate sizes, every shipped (C, G, D) stage shape, against the float64 oracle and the fp32 port."""
+    c, g, d = syn.STAGE_CHANNELS[stage], syn.STAGE_GROUPS[stage], syn.STAGE_NDEPTHS[stage]
+    h, w = syn.stage_shape(h0, w0, stage)
+    b = 2
+    feats = [syn.smooth_features(b, c, h, w, 100 * stage + v) for v in range(n)]
+    proj = syn.proj_matrices(b, n, h0, w0, stage, per_batch_jitter=0.2, tilt_rad=0.01)
+    if stage == 0:
+        hypo = O.init_inverse_range_np(syn.depth_values(b), d, h, w)
+    else:
+        inv = 1.0 / np.stack([syn.smooth_depth_map(h // 2, w // 2, s) for s in range(b)])
+        half = np.float32(0.5 * (1 / 425.0 - 1 / 935.0) / 2 ** stage / 4)
+        hypo = O.schedule_inverse_range_np((inv + half).astype(np.float32), (inv - half).astype(np.float32), d, h, w)
+    vol, wts = mv.epipolar_weights([f.to(DEV) for f in feats], _cuda(proj), _cuda(hypo), g, 2.0)
+    ref64, w64, _ = O.epipolar_aggregate_np(feats[0].numpy(), [f.numpy() for f in feats[1:]], proj, hypo, g, 2.0)
+    assert np.abs(vol.cpu().numpy() - ref64).max() < 1e-4
+    assert np.abs(wts.cpu().numpy() - w64).max() < 1e-4
+    port = O.epipolar_aggregate_port(feats, torch.from_numpy(proj), torch.from_numpy(hypo), g, 2.0)
+    assert np.abs(vol.cpu().numpy() - port.numpy()).max() < 1e-4
+
+
+# --------------------------------------------------------------------------------------------------------------
+# compatibility seams
+# --------------------------------------------------------------------------------------------------------------
+def test_homo_warping_matches_reference(golden):
+    g = golden("warp")
+    out = mv.homo_warping(_cuda(g["src"]), _cuda(g["src_proj"]), _cuda(g["ref_proj"]), _cuda(g["hypo"]))
+    assert out.shape == g["warped"].shape
+    assert np.abs(out.cpu().numpy() - g["warped"]).max() < 1e-4
+
+
+def test_schedule_matches_reference(golden):
+    g = golden("schedule")
+    init = mv.init_inverse_range(_cuda(g["depth_values"]), 8, DEV, torch.float32, 6, 7).cpu().numpy()
+    assert np.abs(init - g["init"]).max() / np.abs(g["init"]).max() < 3e-7
+    for d in (4, 8):
+        s = mv.schedule_inverse_range(_cuda(g["inv_min"]), _cuda(g["inv_max"]), d, 14, 18).cpu().numpy()
+        assert s.shape == g["sched%d" % d].shape
+        assert np.abs(s - g["sched%d" % d]).max() / np.abs(s).max() < 1e-6
+
+
+class _Replay(torch.nn.Module):
+    def __init__(self, logits):
+        super().__init__()
+        self.logits = logits
+        self.seen = None
+
+    def forward(self, x):
+        self.seen = x
+        return self.logits
+
+
+def test_tail_matches_reference(golden):
+    g = golden("tail")
+    b, d, h, w = g["logits"].shape
+    feats = [syn.smooth_features(b, 8, h, w, s, device=DEV) for s in range(2)]
+    proj = _cuda(syn.proj_matrices(b, 2, h, w, 3))
+    for mode in ("eval", "train"):
+        net = mv.stagenet(inverse_depth=True, mono=True, attn_temp=2.0)
+        net = net.eval() if mode == "eval" else net.train()
+        ret = net(feats, proj, _cuda(g["hypo"]), _Replay(_cuda(g["logits"])), 1, group_cor=True, group_cor_dim=4,
+                  split_itv=float(g["split_itv"]))
+        assert list(ret.keys()) == ["depth", "photometric_confidence", "hypo_depth", "attn_weight",
+                                    "inverse_min_depth", "inverse_max_depth", "mono_feat"]
+        assert np.array_equal(ret["depth"].cpu().numpy(), g[mode + "_depth"])
+        assert np.abs(ret["attn_weight"].cpu().numpy() - g[mode + "_attn_weight"]).max() < 1e-6
+        for k in ("inverse_min_depth", "inverse_max_depth"):
+            assert np.abs(ret[k].cpu().numpy() - g[mode + "_" + k]).max() < 1e-9
+        conf = ret["photometric_confidence"].cpu().numpy()
+        if mode == "train":
+            assert conf.shape == () and conf == 0.0
+        else:
+            ok = np.isfinite(g["eval_photometric_confidence"])
+            assert np.allclose(conf[ok], g["eval_photometric_confidence"][ok], rtol=2e-5, atol=1e-6)
+        assert ret["mono_feat"] is feats[0]
+
+
+def test_tail_generic_depth_count_and_regression():
+    rng = np.random.RandomState(0)
+    for d in (3, 5, 16, 48):
+        logits = rng.normal(size=(2, d, 7, 9)).astype(np.float32) * 2
+        hypo = np.sort(rng.uniform(400, 900, size=(2, d, 7, 9)).astype(np.float32), 1)[:, ::-1].copy()
+        for regress in (False, True):
+            want = O.tail_np(logits, hypo, 0.5, regress=regress)
+            attn, depth, conf, lo, hi = ops.tail(_cuda(logits), _cuda(hypo), 0.5, True, True,
+                                                 ops.DEPTH_REGRESS if regress else ops.DEPTH_ARGMAX)
+            assert np.abs(attn.cpu().numpy() - want["attn_weight"]).max() < 1e-6
+            if regress:
+                assert np.abs(depth.cpu().numpy() - want["depth"]).max() < 1e-3
+            else:
+                assert np.array_equal(depth.cpu().numpy(), want["depth"])
+            assert np.allclose(lo.cpu().numpy(), want["inverse_min_depth"], rtol=1e-5, atol=1e-9)
+
+
+def test_tail_backward_matches_torch_softmax():
+    torch.manual_seed(0)
+    logits = torch.randn(2, 8, 6, 5, device=DEV, requires_grad=True)
+    hypo = torch.rand(2, 8, 6, 5, device=DEV) * 500 + 400
+    gw = torch.randn(2, 8, 6, 5, device=DEV)
+    from deep_reconstruction_with_epipolar_lines_mvster_b200.stagenet import _Tail
+    attn, depth, _, _, _ = _Tail.apply(logits, hypo, 0.5, False, True, ops.DEPTH_ARGMAX)
+    (attn * gw).sum().backward()
+    ref = logits.detach().clone().requires_grad_(True)
+    (torch.softmax(ref, 1) * gw).sum().backward()
+    assert (logits.grad - ref.grad).abs().max().item() < 1e-6
+    # regression mode: depth = sum attn * hypo is differentiable too
+    l2 = logits.detach().clone().requires_grad_(True)
+    attn, depth, _, _, _ = _Tail.apply(l2, hypo, 0.5, False, True, ops.DEPTH_REGRESS)
+    ((attn * gw).sum() + depth.sum() * 1e-2).backward()
+    r2 = logits.detach().clone().requires_grad_(True)
+    a = torch.softmax(r2, 1)
+    ((a * gw).sum() + (a * hypo).sum() * 1e-2).backward()
+    assert (l2.grad - r2.grad).abs().max().item() < 1e-4
+
+
+def test_depth_regression(golden):
+    g = golden("tail")
+    p = torch.softmax(_cuda(g["logits"]), 1)
+    got = mv.depth_regression(p, _cuda(g["hypo"]))
+    want = (p * _cuda(g["hypo"])).sum(1)
+    assert (got - want).abs().max().item() < 1e-2 * 1e-1   # ~1e-6 relative on depths of ~600
+
+
+# --------------------------------------------------------------------------------------------------------------
+# teacher-forced cascade through the drop-in stagenet
+# --------------------------------------------------------------------------------------------------------------
+def test_cascade_teacher_forced_matches_reference(golden):
+    g = golden("cascade")
+    net = mv.stagenet(inverse_depth=True, mono=False, attn_fuse_d=True, attn_temp=2.0).eval()
+    for s in range(1, 5):
+        k = "s%d_" % s
+        feats = [_cuda(g[k + "features"][:, v]) for v in range(g[k + "features"].shape[1])]
+        replay = _Replay(_cuda(g[k + "logits"]))
+        with torch.no_grad():
+            ret = net(feats, _cuda(g[k + "proj"]), _cuda(g[k + "hypo"]), replay, s - 1, group_cor=True,
+                      group_cor_dim=int(g[k + "groups"]), split_itv=float(g[k + "split_itv"]))
+        assert np.abs(replay.seen.cpu().numpy() - g[k + "volume"]).max() < 1e-4, "stage %d volume" % s
+        assert np.abs(ret["attn_weight"].cpu().numpy() - g[k + "out_attn_weight"]).max() < 1e-4
+        # teacher-forced logits -> identical arg-max -> depth identical (well inside 1e-3 of the interval)
+        assert np.array_equal(ret["depth"].cpu().numpy(), g[k + "out_depth"])
+        conf_ref = g[k + "out_photometric_confidence"]
+        ok = np.isfinite(conf_ref) & (np.abs(conf_ref) < 1e3)
+        assert np.allclose(ret["photometric_confidence"].cpu().numpy()[ok], conf_ref[ok], rtol=1e-4, atol=1e-5)
+        for name in ("inverse_min_depth", "inverse_max_depth"):
+            assert np.allclose(ret[name].cpu().numpy(), g[k + "out_" + name], rtol=1e-6, atol=1e-10)
+        if s < 4:   # the schedule feeding the next stage
+            kn = "s%d_" % (s + 1)
+            h, w = g[kn + "hypo"].shape[2:]
+            nxt = mv.schedule_inverse_range(ret["inverse_min_depth"], ret["inverse_max_depth"], g[kn + "hypo"].shape[1],
+                                            h, w)
+            assert np.abs(nxt.cpu().numpy() - g[kn + "hypo"]).max() / np.abs(g[kn + "hypo"]).max() < 1e-6
+
+
+# --------------------------------------------------------------------------------------------------------------
+# K2b filter
+# --------------------------------------------------------------------------------------------------------------
+def test_filter_pairs_match_reference(golden):
+    g = golden("filter")
+    cfg = mv.FilterConfig(float(g["condmask_pixel"]), float(g["condmask_depth"]), float(g["photomask"]), int(g["geomask"]))
+    total = same = 0
+    for i, row in enumerate(g["pairs"]):
+        r = int(row[0])
+        for j, s in enumerate(row[1:]):
+            s = int(s)
+            m, d, x2, y2 = mv.check_geometric_consistency(g["depths"][r], g["ks"][r], g["es"][r], g["depths"][s],
+                                                          g["ks"][s], g["es"][s], cfg)
+            assert m.dtype == np.bool_ and d.dtype == np.float32
+            total += m.size
+            same += int((m == g["pair_mask"][i, j]).sum())
+            both = m & g["pair_mask"][i, j]
+            assert np.abs(d[both] - g["pair_depth_reprojected"][i, j][both]).max() < 2e-3
+            assert np.all(d[~m] == 0)
+            fin = np.isfinite(g["pair_x2d_src"][i, j])
+            assert np.abs(x2[fin] - g["pair_x2d_src"][i, j][fin]).max() < 1e-3
+            assert np.abs(y2[fin] - g["pair_y2d_src"][i, j][fin]).max() < 1e-3
+    assert same / total >= 0.9999, same / total
+
+
+def test_filter_fusion_matches_reference(golden):
+    g = golden("filter")
+    cfg = mv.FilterConfig(float(g["condmask_pixel"]), float(g["condmask_depth"]), float(g["photomask"]), int(g["geomask"]))
+    photo, geo, final, avg, gsum = mv.filter_scene(g["depths"], g["conf"], g["ks"], g["es"], g["pairs"], cfg,
+                                                   want_geo_sum=True)
+    assert np.array_equal(photo.cpu().numpy(), g["photo"])
+    assert (geo.cpu().numpy() == g["geo"]).mean() >= 0.9999
+    assert (final.cpu().numpy() == g["final"]).mean() >= 0.9999
+    ok = (gsum.cpu().numpy() == g["geo_sum"]) & np.isfinite(g["depth_avg"])
+    assert ok.mean() > 0.999
+    assert np.abs(avg.cpu().numpy()[ok] - g["depth_avg"][ok]).max() < 2e-3
+    # the reference's read_pair_file structure is accepted as well, ragged source lists included
+    pairs = [(int(r[0]), [int(x) for x in r[1:]]) for r in g["pairs"]]
+    pairs[0] = (pairs[0][0], pairs[0][1][:2])
+    p2, g2, f2, a2, _ = mv.filter_scene(g["depths"], g["conf"], g["ks"], g["es"], pairs, cfg)
+    assert torch.equal(p2[1:], photo[1:]) and torch.equal(g2[1:], geo[1:]) and torch.equal(a2[1:], avg[1:])
+
+
+def test_filter_same_camera_is_identity():
+    h, w = 40, 56
+    k = syn.intrinsics(h, w, 3)
+    e = syn.extrinsics(1)
+    depth = syn.smooth_depth_map(h, w, 2)
+    m, d, x2, y2 = mv.check_geometric_consistency(depth, k, e, depth, k, e, mv.FilterConfig())
+    assert m.all()
+    assert np.abs(d - depth).max() < 1e-3
+    xs, ys = np.meshgrid(np.arange(w), np.arange(h))
+    assert np.abs(x2 - xs).max() < 1e-3 and np.abs(y2 - ys).max() < 1e-3
