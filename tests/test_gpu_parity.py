@@ -279,18 +279,24 @@ def test_cascade_teacher_forced_matches_reference(golden):
                       group_cor_dim=int(g[k + "groups"]), split_itv=float(g[k + "split_itv"]))
         assert np.abs(replay.seen.cpu().numpy() - g[k + "volume"]).max() < 1e-4, "stage %d volume" % s
         assert np.abs(ret["attn_weight"].cpu().numpy() - g[k + "out_attn_weight"]).max() < 1e-4
-        # teacher-forced logits -> identical arg-max -> depth identical (well inside 1e-3 of the interval)
-        assert np.array_equal(ret["depth"].cpu().numpy(), g[k + "out_depth"])
+        # teacher-forced logits -> identical arg-max -> identical depth, except where the reference's own top-2
+        # softmax values are within fp32 rounding of each other (random-init regnet: nearly flat logits)
+        srt = np.sort(g[k + "out_attn_weight"], 1)
+        decided = (srt[:, -1] - srt[:, -2]) > 1e-6
+        same = ret["depth"].cpu().numpy() == g[k + "out_depth"]
+        assert same[decided].all(), "stage %d: arg-max differs on a decided pixel" % s
+        assert same.mean() > 0.97, "stage %d flip fraction %.4f" % (s, 1 - same.mean())
+        same_nb = same
         conf_ref = g[k + "out_photometric_confidence"]
         ok = np.isfinite(conf_ref) & (np.abs(conf_ref) < 1e3)
         assert np.allclose(ret["photometric_confidence"].cpu().numpy()[ok], conf_ref[ok], rtol=1e-4, atol=1e-5)
         for name in ("inverse_min_depth", "inverse_max_depth"):
-            assert np.allclose(ret[name].cpu().numpy(), g[k + "out_" + name], rtol=1e-6, atol=1e-10)
-        if s < 4:   # the schedule feeding the next stage
+            assert np.allclose(ret[name].cpu().numpy()[same_nb], g[k + "out_" + name][same_nb], rtol=1e-6, atol=1e-10)
+        if s < 4:   # the schedule feeding the next stage (teacher-forced with the reference's inverse range)
             kn = "s%d_" % (s + 1)
             h, w = g[kn + "hypo"].shape[2:]
-            nxt = mv.schedule_inverse_range(ret["inverse_min_depth"], ret["inverse_max_depth"], g[kn + "hypo"].shape[1],
-                                            h, w)
+            nxt = mv.schedule_inverse_range(_cuda(g[k + "out_inverse_min_depth"]), _cuda(g[k + "out_inverse_max_depth"]),
+                                            g[kn + "hypo"].shape[1], h, w)
             assert np.abs(nxt.cpu().numpy() - g[kn + "hypo"]).max() / np.abs(g[kn + "hypo"]).max() < 1e-6
 
 
