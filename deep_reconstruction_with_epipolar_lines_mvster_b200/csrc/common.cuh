@@ -89,6 +89,76 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, new on sm_100): one issue slot for two lanes of math --------
+typedef unsigned long long f32x2;  // two floats in one 64-bit register pair (lo = even channel, hi = odd channel)
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// 8 channels of one texel as 4 packed pairs
+struct P8 {
+    f32x2 q[4];
+};
+
+// 256-bit read-only load straight into four 64-bit register pairs (LDG.E.256)
+__device__ __forceinline__ P8 ldg256_pairs(const void* p) {
+    P8 r;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.q[0]), "=l"(r.q[1]), "=l"(r.q[2]), "=l"(r.q[3])
+                 : "l"(p));
+    return r;
+}
+// 8 bf16 channels (16 bytes) widened to 4 packed fp32 pairs
+__device__ __forceinline__ P8 ldg_bf16x8_pairs(const void* p) {
+    uint4 q;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p));
+    P8 r;
+    r.q[0] = pack2(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u));
+    r.q[1] = pack2(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+    r.q[2] = pack2(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u));
+    r.q[3] = pack2(__uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ P8 load_pairs(const void* p);
+template <>
+__device__ __forceinline__ P8 load_pairs<float>(const void* p) {
+    return ldg256_pairs(p);
+}
+template <>
+__device__ __forceinline__ P8 load_pairs<__nv_bfloat16>(const void* p) {
+    return ldg_bf16x8_pairs(p);
+}
+
+// 1/x to <= 1 ulp without the IEEE-division slow path: MUFU.RCP + one Newton step
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    const float e = fmaf(-x, r, 1.0f);
+    return fmaf(r, e, r);
+}
+
 // Per-(batch, view) homography [R | t], 12 floats, uniform across a CTA.
 struct Homography {
     float r00, r01, r02, t0, r10, r11, r12, t1, r20, r21, r22, t2;

@@ -3,21 +3,67 @@
 // volume, the repeated reference volume and the per-view correlation volumes of the reference
 // (models/mvs4net_utils.py:1036,1051,1066-1069,1083-1085,1100) never exist in memory.
 //
-// Work decomposition (sm_100a):
-//   * features are NHWC; a lane owns 8 consecutive channels of one reference pixel, so every bilinear tap is a
-//     single 32-byte LDG.E.256 (fp32) / 16-byte LDG.E.128 (bf16) and the lanes of a warp read one contiguous
-//     ~1 KB span of the source row (adjacent pixels hit adjacent texels);
-//   * L = C/8 lanes cooperate on one pixel (L = 1, 2, 4, 8 for C = 8, 16, 32, 64); a lane's 8 channels cover
-//     8/(C/G) whole correlation groups, so the group correlation is lane-local and only the per-hypothesis score
-//     (sum over groups) crosses lanes, with log2(L) xor-shuffles;
-//   * the softmax over D, the running sum of weights and the weighted volume accumulators live in registers;
-//   * a CTA is 8 warps stacked in y (a (32/L) x 8 pixel tile) so that the y0+1 source row fetched for one
-//     reference row is still in L1 when the next row needs it as y0.
+// Work decomposition (sm_100a).  Features are NHWC, so a bilinear tap is one contiguous channel vector.
+// A lane owns CH channels (a multiple of 8) x DL depth hypotheses of one reference pixel; L = (C/CH)*(D/DL) lanes
+// cooperate on a pixel.  Splitting the *hypotheses* across lanes (not only the channels) means that every lane
+// does its own sample-position arithmetic - no redundant coordinate math for the wide coarse stages (C = 32/64).
+//   - group correlation is lane-local (a lane's channels cover whole groups); the per-hypothesis score is summed
+//     over the C/CH channel lanes, the softmax max / sum over the D/DL hypothesis lanes, both with xor-shuffles;
+//   - bilinear blending and ref*warped products run as packed fp32x2 (FFMA2 / FMUL2), two channels per issue slot;
+//   - the softmax over D, the running weight sum and the weighted volume accumulators live in registers.
+//
+// Two tap sources:
+//   DIRECT (any C, fp32 or bf16): 32-byte LDG.E.256 (fp32) / 16-byte LDG.E.128 (bf16) per 8 channels straight from
+//     global memory through L1, per-tap bounds weights.  Texels of C >= 32 fp32 channels are whole 128-byte
+//     lines, which the L1 data pipe serves at full rate.
+//   TMA (C = 8 or 16 fp32, i.e. 32/64-byte texels): direct gathers of sub-line texels waste the L1 data pipe
+//     (a wavefront serves one 128-byte line; unaligned texel runs straddle lines - measured 22 wavefronts per
+//     LDG.E.256).  A CTA owns a 32x8 / 32x4 pixel tile and, per source view, (1) reduces its sample positions to an
+//     integer bounding box (REDUX.MIN/MAX + 4 shared atomics), (2) has one thread issue ONE cp.async.bulk.tensor.4d
+//     of box {C, BW, BH, 1} into shared memory (mbarrier completion; TMA zero-fills outside the image, which IS
+//     grid_sample's padding_mode='zeros', so the gather needs no bounds logic), (3) gathers with LDS.128 from the
+//     hardware-swizzled box (SWIZZLE_32B/64B: 8 neighbouring texels hit 8 different bank groups).  The box of view
+//     v+1 is requested before the gather of view v (two buffers).  A tile whose footprint exceeds the box falls
+//     back to direct gathers for that view.
+#include <cuda.h>
+#include <limits.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvster {
 
+// ---------------------------------------------------------------------------------------------------------------------
+// lane decomposition of the TMA-staged kernel: one lane owns all C <= 16 channels and all D hypotheses of a pixel
+// ---------------------------------------------------------------------------------------------------------------------
+template <int C, int CPG, int D>
+struct Split {
+    static constexpr int CH = C;                           // channels per lane
+    static constexpr int GPL = CH / CPG;                   // correlation groups per lane
+    static constexpr int DL = D;                           // hypotheses per lane
+    static constexpr int LC = 1, LD = 1, L = 1;            // lanes per pixel
+    static constexpr int PPW = 32;                         // pixels per warp
+    static constexpr int NCHUNK = CH / 8;                  // 8-channel chunks per lane
+    static constexpr int WX = 1;                           // warps side by side in x (8 warps per CTA)
+    static constexpr int TILE_W = 32, TILE_H = 8;
+    static_assert(CH % 8 == 0 && 8 % CPG == 0, "a lane's 8-channel chunks must hold whole groups");
+};
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+template <int C>
+struct TmaGeom {
+    static constexpr int TB = C * 4;  // texel bytes (32 or 64)
+    // staging box in texels; the width is a multiple of 8 so that the swizzle phase depends on x only.  Sized for
+    // ~25 % scale change / a dozen texels of epipolar span across a tile; larger footprints take the direct path.
+    static constexpr int BW = 48;
+    static constexpr int CTL_BYTES = 16 /* 2 mbarriers */ + 48 /* 3 bbox slots */;
+    static constexpr int BH_EXTRA = 6;  // box height = tile height + BH_EXTRA
+};
+
 struct EpiFwdParams {
+    CUtensorMap tmap[MVSTER_MAX_SRC_VIEWS];  // TMA variant only
     const void* ref;
     const void* src[MVSTER_MAX_SRC_VIEWS];
     const float* rt;
@@ -30,106 +76,501 @@ struct EpiFwdParams {
     float inv_sqrt_c;   // 1 / sqrt(C)
 };
 
-constexpr int kWarpsPerCta = 8;
+// ---------------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void lds_pairs(uint32_t addr, f32x2& a, f32x2& b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-template <int C, int CPG, int D, typename T>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
-    constexpr int CPL = 8;          // channels per lane
-    constexpr int L = C / CPL;      // lanes per pixel
-    constexpr int GPL = CPL / CPG;  // correlation groups per lane
-    constexpr int PPW = 32 / L;     // pixels per warp
+// Horizontal sum of the channels of correlation group g (0 .. 8/CPG-1) of one 8-channel chunk of products.
+template <int CPG>
+__device__ __forceinline__ float group_sum(const f32x2 (&prod)[4], int g) {
+    float lo, hi;
+    if constexpr (CPG == 1) {
+        unpack2(prod[g >> 1], lo, hi);
+        return (g & 1) ? hi : lo;
+    } else if constexpr (CPG == 2) {
+        unpack2(prod[g], lo, hi);
+        return lo + hi;
+    } else if constexpr (CPG == 4) {
+        unpack2(add2(prod[2 * g], prod[2 * g + 1]), lo, hi);
+        return lo + hi;
+    } else {
+        unpack2(add2(add2(prod[0], prod[1]), add2(prod[2], prod[3])), lo, hi);
+        return lo + hi;
+    }
+}
+
+// Sample position of one hypothesis, clamped to [-1, Ws] x [-1, Hs].  A clamped coordinate has both of its taps
+// outside the image (or a zero weight on the one inside), so the sample contributes nothing - exactly like the
+// unclamped out-of-range sample under padding_mode='zeros' - while staying next to the image for the bounding box.
+// NaN collapses to -1 (the CPU reference samples nothing for NaN coordinates either).
+// p = R*[x,y,1]*d + t ; z==0 -> 1e-9 ; p.xy / z                                         (reference :42-48)
+__device__ __forceinline__ void sample_pos(float ax, float ay, float az, const Homography& h, float d, float wlim,
+                                           float hlim, float& sx, float& sy) {
+    const float px = fmaf(ax, d, h.t0);
+    const float py = fmaf(ay, d, h.t1);
+    float pz = fmaf(az, d, h.t2);
+    pz = (pz == 0.0f) ? 1e-9f : pz;
+    const float rz = fast_rcp(pz);
+    sx = fminf(fmaxf(px * rz, -1.0f), wlim);
+    sy = fminf(fmaxf(py * rz, -1.0f), hlim);
+}
+
+__device__ __forceinline__ Homography homography_from_smem(const float* rt_s) {
+    const float4* hq = reinterpret_cast<const float4*>(rt_s);
+    const float4 h0 = hq[0], h1 = hq[1], h2 = hq[2];
+    Homography h;
+    h.r00 = h0.x; h.r01 = h0.y; h.r02 = h0.z; h.t0 = h0.w;
+    h.r10 = h1.x; h.r11 = h1.y; h.r12 = h1.z; h.t1 = h1.w;
+    h.r20 = h2.x; h.r21 = h2.y; h.r22 = h2.z; h.t2 = h2.w;
+    return h;
+}
+
+// blend four taps of one 8-channel chunk, multiply with the (pre-scaled) reference chunk, add the per-group sums
+template <int CPG>
+__device__ __forceinline__ void blend_correlate(const P8& t00, const P8& t01, const P8& t10, const P8& t11, float w00,
+                                                float w01, float w10, float w11, const f32x2* rf, float* cor_out) {
+    const f32x2 p00 = pack2(w00, w00), p01 = pack2(w01, w01), p10 = pack2(w10, w10), p11 = pack2(w11, w11);
+    f32x2 prod[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        f32x2 wv = mul2(p00, t00.q[q]);
+        wv = fma2(p01, t01.q[q], wv);
+        wv = fma2(p10, t10.q[q], wv);
+        wv = fma2(p11, t11.q[q], wv);
+        prod[q] = mul2(rf[q], wv);  // ref * warped, per channel
+    }
+#pragma unroll
+    for (int g = 0; g < 8 / CPG; ++g) cor_out[g] = group_sum<CPG>(prod, g);  // reference :1066-1069
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------------
+template <int C, int CPG, int D, bool TMA, typename T>
+__global__ void __launch_bounds__(kThreads, 2) epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
+    using S = Split<C, CPG, D>;
+    constexpr int CH = S::CH, DL = S::DL, LC = S::LC, L = S::L, PPW = S::PPW, GPL = S::GPL, NCHUNK = S::NCHUNK;
     constexpr int G = C / CPG;
-    static_assert(C % CPL == 0 && CPL % CPG == 0 && L >= 1 && L <= 32, "unsupported channel split");
+    constexpr int WX = S::WX, TILE_H = S::TILE_H;  // CTA tile: 32 x 8 pixels
+    constexpr int TB = C * (int)sizeof(T); // texel bytes
+    static_assert(!TMA || (sizeof(T) == 4 && (C == 8 || C == 16) && LC == 1 && S::TILE_W == 32), "TMA variant: fp32, C in {8,16}");
 
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int sub = lane % L;  // which 8-channel chunk of the pixel
+    extern __shared__ unsigned char smem_raw[];
+    // TMA variant: [buf0 | buf1] 1024-aligned, then 2 mbarriers + 3 bbox slots; both variants: homographies at the end
+    constexpr int BH = (TILE_H + TmaGeom<C>::BH_EXTRA);
+    constexpr int BUF_BYTES = TMA ? TmaGeom<C>::BW * BH * TB : 0;
+    constexpr int ROW_BYTES = TmaGeom<C>::BW * TB;
+    const uint32_t smem_base = TMA ? ((smem_u32(smem_raw) + 1023u) & ~1023u) : smem_u32(smem_raw);
+    const uint32_t ctl = smem_base + 2u * BUF_BYTES;
+    unsigned char* ctl_ptr = smem_raw + (ctl - smem_u32(smem_raw));
+    int* bbox = reinterpret_cast<int*>(ctl_ptr + 16);                                  // [3][4] (TMA only)
+    float* rt_s = reinterpret_cast<float*>(ctl_ptr + (TMA ? TmaGeom<C>::CTL_BYTES : 0));  // [Nsrc][12]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int pix = lane / L;
+    const int cl = lane % LC;         // channel chunk of this lane
+    const int dl = (lane % L) / LC;   // hypothesis chunk of this lane
     const int b = blockIdx.z;
-    int x = blockIdx.x * PPW + pix;
-    int y = blockIdx.y * kWarpsPerCta + warp;
+    if (tid < p.Nsrc * 12) rt_s[tid] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + tid);
+    int x = blockIdx.x * S::TILE_W + (warp % WX) * PPW + pix;
+    int y = blockIdx.y * TILE_H + (warp / WX);
     const bool live = (x < p.W) && (y < p.H);
-    // dead lanes shadow a valid pixel so that warp shuffles stay convergent; their stores are masked
-    x = min(x, p.W - 1);
+    x = min(x, p.W - 1);  // dead lanes shadow a valid pixel: shuffles stay convergent, the bounding box is unaffected
     y = min(y, p.H - 1);
+
+    if constexpr (TMA) {
+        if (tid == 0) {
+            mbar_init(ctl, 1);
+            mbar_init(ctl + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                bbox[i * 4 + 0] = INT_MAX; bbox[i * 4 + 1] = INT_MAX;
+                bbox[i * 4 + 2] = INT_MIN; bbox[i * 4 + 3] = INT_MIN;
+            }
+        }
+    }
+    __syncthreads();
 
     const size_t plane = (size_t)p.H * p.W;
     const size_t pix_off = (size_t)y * p.W + x;
 
-    // reference feature chunk: 8 channels, pre-scaled by 1/(C/G) so the group mean is a plain dot product
-    const T* refp = reinterpret_cast<const T*>(p.ref) + (((size_t)b * plane + pix_off) * C + sub * CPL);
-    F8 rf = load8<T>(refp);
+    // reference channels of this lane as packed pairs, pre-scaled by 1/(C/G) so the group mean is a plain sum
+    f32x2 rf[NCHUNK * 4];
+    {
+        const T* refp = reinterpret_cast<const T*>(p.ref) + (((size_t)b * plane + pix_off) * C + cl * CH);
+        const f32x2 sc = pack2(1.0f / CPG, 1.0f / CPG);
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) rf.v[c] *= (1.0f / CPG);
-
-    float hyp[D];
+        for (int k = 0; k < NCHUNK; ++k) {
+            const P8 r = load_pairs<T>(refp + k * 8);
 #pragma unroll
-    for (int d = 0; d < D; ++d) hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + d) * plane + pix_off);
+            for (int q = 0; q < 4; ++q) rf[k * 4 + q] = mul2(r.q[q], sc);
+        }
+    }
+    float hyp[DL];
+#pragma unroll
+    for (int d = 0; d < DL; ++d) hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + dl * DL + d) * plane + pix_off);
 
-    float acc[GPL][D];
-    float wsum[D];
+    float acc[GPL][DL], wsum[DL];
+#pragma unroll
+    for (int d = 0; d < DL; ++d) {
+        wsum[d] = 1e-8f;  // reference :1037
+#pragma unroll
+        for (int g = 0; g < GPL; ++g) acc[g][d] = 0.0f;
+    }
+
+    const float fxp = (float)x, fyp = (float)y;
+    const float wlim = (float)p.Ws, hlim = (float)p.Hs;
+    const size_t lane_src_off = ((size_t)b * p.Hs * p.Ws * C + cl * CH) * sizeof(T);
+
+    // ---- TMA staging state (one view ahead) ----------------------------------------------------------------------
+    float nsx[DL], nsy[DL];
+    int nbx = 0, nby = 0;
+    bool nfit = false;
+    uint32_t uses0 = 0, uses1 = 0;  // completed phases of the two mbarriers (uniform across the CTA)
+
+    auto positions = [&](int v, float* sx, float* sy) {
+        const Homography h = homography_from_smem(rt_s + v * 12);
+        // R * [x, y, 1]^T, shared by all hypotheses of this pixel (reference :42)
+        const float ax = fmaf(h.r00, fxp, fmaf(h.r01, fyp, h.r02));
+        const float ay = fmaf(h.r10, fxp, fmaf(h.r11, fyp, h.r12));
+        const float az = fmaf(h.r20, fxp, fmaf(h.r21, fyp, h.r22));
+#pragma unroll
+        for (int d = 0; d < DL; ++d) sample_pos(ax, ay, az, h, hyp[d], wlim, hlim, sx[d], sy[d]);
+    };
+
+    auto stage_view = [&](int v) {  // TMA only: positions of view v, CTA bounding box, TMA request; one __syncthreads()
+        positions(v, nsx, nsy);
+        float lox = nsx[0], hix = nsx[0], loy = nsy[0], hiy = nsy[0];
+#pragma unroll
+        for (int d = 1; d < DL; ++d) {
+            lox = fminf(lox, nsx[d]); hix = fmaxf(hix, nsx[d]);
+            loy = fminf(loy, nsy[d]); hiy = fmaxf(hiy, nsy[d]);
+        }
+        const int slot = v % 3;
+        const int wx0 = __reduce_min_sync(0xffffffffu, __float2int_rd(lox));
+        const int wy0 = __reduce_min_sync(0xffffffffu, __float2int_rd(loy));
+        const int wx1 = __reduce_max_sync(0xffffffffu, __float2int_rd(hix));
+        const int wy1 = __reduce_max_sync(0xffffffffu, __float2int_rd(hiy));
+        if (lane == 0) {
+            atomicMin(&bbox[slot * 4 + 0], wx0); atomicMin(&bbox[slot * 4 + 1], wy0);
+            atomicMax(&bbox[slot * 4 + 2], wx1); atomicMax(&bbox[slot * 4 + 3], wy1);
+        }
+        if (tid == 0) {  // recycle the slot that view v+1 will use (its last readers passed the previous barrier)
+            const int nx = (v + 1) % 3;
+            bbox[nx * 4 + 0] = INT_MAX; bbox[nx * 4 + 1] = INT_MAX;
+            bbox[nx * 4 + 2] = INT_MIN; bbox[nx * 4 + 3] = INT_MIN;
+        }
+        __syncthreads();  // bbox complete; every thread has also finished gathering from buffer v&1 (view v-2)
+        const int4 bb = *reinterpret_cast<const int4*>(&bbox[slot * 4]);
+        nbx = bb.x; nby = bb.y;
+        nfit = (bb.z - bb.x + 2 <= TmaGeom<C>::BW) && (bb.w - bb.y + 2 <= BH);  // +1 for the right / bottom tap
+        if (nfit && tid == 0) {
+            const uint32_t bar = ctl + 8u * (v & 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+            mbar_expect_tx(bar, (uint32_t)BUF_BYTES);
+            tma_load_4d(smem_base + (uint32_t)BUF_BYTES * (v & 1), &p.tmap[v], bar, 0, nbx, nby, b);
+        }
+    };
+
+    if constexpr (TMA) stage_view(0);
+
+#pragma unroll 1
+    for (int v = 0; v < p.Nsrc; ++v) {
+        float sx[DL], sy[DL];
+        int bx = 0, by = 0;
+        bool fit = false;
+        if constexpr (TMA) {
+#pragma unroll
+            for (int d = 0; d < DL; ++d) { sx[d] = nsx[d]; sy[d] = nsy[d]; }
+            bx = nbx; by = nby; fit = nfit;
+            if (v + 1 < p.Nsrc) stage_view(v + 1);
+        } else {
+            positions(v, sx, sy);
+        }
+
+        float cor[GPL][DL];
+        if (TMA && fit) {
+            // ---- gather from the swizzled shared-memory box (zero-filled outside the image) --------------------------
+            const uint32_t parity = ((v & 1) ? uses1 : uses0) & 1u;
+            mbar_wait(ctl + 8u * (v & 1), parity);
+            if (v & 1) ++uses1; else ++uses0;
+            const uint32_t buf = smem_base + (uint32_t)BUF_BYTES * (v & 1);
+            constexpr uint32_t SWZ = (uint32_t)(TB / 16 - 1) << 4;  // swizzled chunk-index bits: [4] or [5:4]
+#pragma unroll
+            for (int d = 0; d < DL; ++d) {
+                const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
+                const float fx = sx[d] - x0f, fy = sy[d] - y0f;
+                const int rx = (int)x0f - bx, ry = (int)y0f - by;
+                const uint32_t xo = (uint32_t)rx * TB;  // byte offset of the left texel inside its row
+                const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + xo;
+                // hardware swizzle: 16-byte chunk index ^= address bits [8:7] (64B mode) / [7] (32B mode); rows are a
+                // multiple of 512 bytes and the buffer is 1024-aligned, so those bits come from the x offset only
+                const uint32_t mA = (xo >> 3) & SWZ, mB = ((xo + TB) >> 3) & SWZ;
+                const float gx = 1.0f - fx, gy = 1.0f - fy;
+                const float w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
+#pragma unroll
+                for (int k = 0; k < NCHUNK; ++k) {
+                    const uint32_t aL = (base + 32u * k) ^ mA, aR = (base + TB + 32u * k) ^ mB;
+                    P8 t00, t01, t10, t11;
+                    lds_pairs(aL, t00.q[0], t00.q[1]);
+                    lds_pairs(aL ^ 16u, t00.q[2], t00.q[3]);
+                    lds_pairs(aR, t01.q[0], t01.q[1]);
+                    lds_pairs(aR ^ 16u, t01.q[2], t01.q[3]);
+                    lds_pairs(aL + ROW_BYTES, t10.q[0], t10.q[1]);
+                    lds_pairs((aL ^ 16u) + ROW_BYTES, t10.q[2], t10.q[3]);
+                    lds_pairs(aR + ROW_BYTES, t11.q[0], t11.q[1]);
+                    lds_pairs((aR ^ 16u) + ROW_BYTES, t11.q[2], t11.q[3]);
+                    float cg[8 / CPG];
+                    blend_correlate<CPG>(t00, t01, t10, t11, w00, w01, w10, w11, rf + k * 4, cg);
+#pragma unroll
+                    for (int g = 0; g < 8 / CPG; ++g) cor[k * (8 / CPG) + g][d] = cg[g];
+                }
+            }
+        } else {
+            // ---- direct gather from global memory, per-tap bounds weights --------------------------------------------
+            const char* srcp = reinterpret_cast<const char*>(p.src[v]) + lane_src_off;
+#pragma unroll
+            for (int d = 0; d < DL; ++d) {
+                const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
+                const float fx = sx[d] - x0f, fy = sy[d] - y0f;
+                const int x0 = (int)x0f, y0 = (int)y0f;  // in [-1, Ws] x [-1, Hs] after the clamp
+                const bool vx0 = (unsigned)x0 < (unsigned)p.Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)p.Ws;
+                const bool vy0 = (unsigned)y0 < (unsigned)p.Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)p.Hs;
+                const int xc0 = min(max(x0, 0), p.Ws - 1), xc1 = min(x0 + 1, p.Ws - 1);
+                const int yc0 = min(max(y0, 0), p.Hs - 1), yc1 = min(y0 + 1, p.Hs - 1);
+                const float gx = vx0 ? 1.0f - fx : 0.0f, hx = vx1 ? fx : 0.0f;
+                const float gy = vy0 ? 1.0f - fy : 0.0f, hy = vy1 ? fy : 0.0f;
+                const float w00 = gx * gy, w01 = hx * gy, w10 = gx * hy, w11 = hx * hy;
+                // texel index < 2^31 / C (checked on the host): 32-bit index, one IMAD.WIDE.U32 per address
+                const unsigned r0 = (unsigned)(yc0 * p.Ws), r1 = (unsigned)(yc1 * p.Ws);
+                const char* a00 = srcp + (size_t)(r0 + (unsigned)xc0) * TB;
+                const char* a01 = srcp + (size_t)(r0 + (unsigned)xc1) * TB;
+                const char* a10 = srcp + (size_t)(r1 + (unsigned)xc0) * TB;
+                const char* a11 = srcp + (size_t)(r1 + (unsigned)xc1) * TB;
+#pragma unroll
+                for (int k = 0; k < NCHUNK; ++k) {
+                    constexpr int KO = 8 * (int)sizeof(T);
+                    const P8 t00 = load_pairs<T>(a00 + k * KO), t01 = load_pairs<T>(a01 + k * KO);
+                    const P8 t10 = load_pairs<T>(a10 + k * KO), t11 = load_pairs<T>(a11 + k * KO);
+                    float cg[8 / CPG];
+                    blend_correlate<CPG>(t00, t01, t10, t11, w00, w01, w10, w11, rf + k * 4, cg);
+#pragma unroll
+                    for (int g = 0; g < 8 / CPG; ++g) cor[k * (8 / CPG) + g][d] = cg[g];
+                }
+            }
+        }
+
+        // score[d] = sum over all G groups (reference cor_feat.sum(1), :1083): lane-local, then the channel lanes
+        float score[DL];
+#pragma unroll
+        for (int d = 0; d < DL; ++d) {
+            float s = cor[0][d];
+#pragma unroll
+            for (int g = 1; g < GPL; ++g) s += cor[g][d];
+            score[d] = s;
+        }
+#pragma unroll
+        for (int m = 1; m < LC; m <<= 1) {
+#pragma unroll
+            for (int d = 0; d < DL; ++d) score[d] += __shfl_xor_sync(0xffffffffu, score[d], m);
+        }
+        // softmax over D of score / attn_temp, then / sqrt(C); max and sum cross the hypothesis lanes
+        float mx = score[0];
+#pragma unroll
+        for (int d = 1; d < DL; ++d) mx = fmaxf(mx, score[d]);
+#pragma unroll
+        for (int m = LC; m < L; m <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        float e[DL], es = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DL; ++d) {
+            e[d] = ex2_approx((score[d] - mx) * p.score_scale);
+            es += e[d];
+        }
+#pragma unroll
+        for (int m = LC; m < L; m <<= 1) es += __shfl_xor_sync(0xffffffffu, es, m);
+        const float norm = __fdividef(p.inv_sqrt_c, es);
+#pragma unroll
+        for (int d = 0; d < DL; ++d) {
+            const float w = e[d] * norm;
+            wsum[d] += w;
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) acc[g][d] = fmaf(w, cor[g][d], acc[g][d]);
+            if (p.weights != nullptr && cl == 0 && live)
+                p.weights[(((size_t)b * p.Nsrc + v) * D + dl * DL + d) * plane + pix_off] = w;
+        }
+    }
+
+    if (!live) return;
+#pragma unroll
+    for (int d = 0; d < DL; ++d) {
+        const float inv = __frcp_rn(wsum[d]);
+        const int dd = dl * DL + d;
+#pragma unroll
+        for (int g = 0; g < GPL; ++g)
+            stg_stream(p.out + (((size_t)b * G + cl * GPL + g) * D + dd) * plane + pix_off, acc[g][d] * inv);
+        if (p.wsum != nullptr && cl == 0) p.wsum[((size_t)b * D + dd) * plane + pix_off] = wsum[d];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// DIRECT kernel (any C, fp32 / bf16): L = C/8 lanes per pixel, each owning 8 channels, so that the lanes of a pixel
+// read one texel as a single contiguous run - whole 128-byte lines per L1 wavefront for C >= 32.  The sample
+// arithmetic is NOT repeated by every lane: lane j of a pixel computes the positions, tap indices and bilinear
+// weights of hypotheses d = j, j+L, ... only ("owner"), and the D samples are then broadcast inside the pixel's
+// lane group with width-L shuffles (8 values per sample).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int C, int CPG, int D, typename T>
+__global__ void __launch_bounds__(kThreads, 2) epi_fwd_direct_kernel(const __grid_constant__ EpiFwdParams p) {
+    constexpr int L = C / 8, PPW = 32 / L, GPL = 8 / CPG, G = C / CPG;
+    constexpr int NOWN = (D + L - 1) / L;               // samples whose coordinates this lane computes
+    constexpr int WX = L < 8 ? L : 8, TILE_W = PPW * WX, TILE_H = 8 / WX;
+    constexpr int TB = C * (int)sizeof(T);
+    static_assert(L >= 1 && L <= 8 && 8 % CPG == 0, "C in {8,16,32,64}, C/G in {1,2,4,8}");
+
+    extern __shared__ unsigned char smem_raw[];
+    float* rt_s = reinterpret_cast<float*>(smem_raw);  // [Nsrc][12]
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int pix = lane / L, sub = lane % L;
+    const int b = blockIdx.z;
+    if (tid < p.Nsrc * 12) rt_s[tid] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + tid);
+    int x = blockIdx.x * TILE_W + (warp % WX) * PPW + pix;
+    int y = blockIdx.y * TILE_H + (warp / WX);
+    const bool live = (x < p.W) && (y < p.H);
+    x = min(x, p.W - 1);  // dead lanes shadow a valid pixel so that shuffles stay convergent
+    y = min(y, p.H - 1);
+    __syncthreads();
+
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t pix_off = (size_t)y * p.W + x;
+
+    f32x2 rf[4];
+    {
+        const P8 r = load_pairs<T>(reinterpret_cast<const T*>(p.ref) + (((size_t)b * plane + pix_off) * C + sub * 8));
+        const f32x2 sc = pack2(1.0f / CPG, 1.0f / CPG);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rf[q] = mul2(r.q[q], sc);
+    }
+    float hyp[NOWN];
+#pragma unroll
+    for (int k = 0; k < NOWN; ++k) {
+        const int d = min(sub + k * L, D - 1);
+        hyp[k] = ldg_stream(p.hypo + ((size_t)b * D + d) * plane + pix_off);
+    }
+    float acc[GPL][D], wsum[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         wsum[d] = 1e-8f;  // reference :1037
 #pragma unroll
         for (int g = 0; g < GPL; ++g) acc[g][d] = 0.0f;
     }
-
-    const float fx = (float)x, fy = (float)y;
-    const size_t src_batch = (size_t)b * p.Hs * p.Ws * C + sub * CPL;
+    const float fxp = (float)x, fyp = (float)y;
+    const float wlim = (float)p.Ws, hlim = (float)p.Hs;
+    const size_t lane_src_off = ((size_t)b * p.Hs * p.Ws * C + sub * 8) * sizeof(T);
 
 #pragma unroll 1
     for (int v = 0; v < p.Nsrc; ++v) {
-        const Homography h = load_homography(p.rt + ((size_t)b * p.Nsrc + v) * 12);
-        const T* srcp = reinterpret_cast<const T*>(p.src[v]) + src_batch;
-        // R * [x, y, 1]^T, shared by all hypotheses of this pixel (reference :42)
-        const float ax = fmaf(h.r00, fx, fmaf(h.r01, fy, h.r02));
-        const float ay = fmaf(h.r10, fx, fmaf(h.r11, fy, h.r12));
-        const float az = fmaf(h.r20, fx, fmaf(h.r21, fy, h.r22));
-
-        float cor[GPL][D];
-        float score[D];
+        // ---- owner phase: tap texel indices and weights of this lane's own hypotheses -----------------------------
+        unsigned ti[NOWN][4];
+        float tw[NOWN][4];
+        {
+            const Homography h = homography_from_smem(rt_s + v * 12);
+            const float ax = fmaf(h.r00, fxp, fmaf(h.r01, fyp, h.r02));  // R * [x, y, 1]^T (reference :42)
+            const float ay = fmaf(h.r10, fxp, fmaf(h.r11, fyp, h.r12));
+            const float az = fmaf(h.r20, fxp, fmaf(h.r21, fyp, h.r22));
+#pragma unroll
+            for (int k = 0; k < NOWN; ++k) {
+                float sx, sy;
+                sample_pos(ax, ay, az, h, hyp[k], wlim, hlim, sx, sy);
+                const float x0f = floorf(sx), y0f = floorf(sy);
+                const float fx = sx - x0f, fy = sy - y0f;
+                const int x0 = (int)x0f, y0 = (int)y0f;  // in [-1, Ws] x [-1, Hs] after the clamp
+                const bool vx0 = (unsigned)x0 < (unsigned)p.Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)p.Ws;
+                const bool vy0 = (unsigned)y0 < (unsigned)p.Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)p.Hs;
+                const int xc0 = min(max(x0, 0), p.Ws - 1), xc1 = min(x0 + 1, p.Ws - 1);
+                const int yc0 = min(max(y0, 0), p.Hs - 1), yc1 = min(y0 + 1, p.Hs - 1);
+                const float gx = vx0 ? 1.0f - fx : 0.0f, hx = vx1 ? fx : 0.0f;
+                const float gy = vy0 ? 1.0f - fy : 0.0f, hy = vy1 ? fy : 0.0f;
+                tw[k][0] = gx * gy; tw[k][1] = hx * gy; tw[k][2] = gx * hy; tw[k][3] = hx * hy;
+                const unsigned r0 = (unsigned)(yc0 * p.Ws), r1 = (unsigned)(yc1 * p.Ws);
+                ti[k][0] = r0 + (unsigned)xc0; ti[k][1] = r0 + (unsigned)xc1;
+                ti[k][2] = r1 + (unsigned)xc0; ti[k][3] = r1 + (unsigned)xc1;
+            }
+        }
+        // ---- gather phase: every lane fetches its 8 channels of each sample's four taps ---------------------------
+        const char* srcp = reinterpret_cast<const char*>(p.src[v]) + lane_src_off;
+        float cor[GPL][D], score[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const Taps t = make_taps(ax, ay, az, h, hyp[d], p.Hs, p.Ws);
-            float wv[CPL];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) wv[c] = 0.0f;
-            if (t.any) {
-                const F8 a = load8<T>(srcp + (size_t)t.o00 * C);
-                const F8 bq = load8<T>(srcp + (size_t)t.o01 * C);
-                const F8 cq = load8<T>(srcp + (size_t)t.o10 * C);
-                const F8 dq = load8<T>(srcp + (size_t)t.o11 * C);
-#pragma unroll
-                for (int c = 0; c < CPL; ++c)
-                    wv[c] = fmaf(t.w00, a.v[c], fmaf(t.w01, bq.v[c], fmaf(t.w10, cq.v[c], t.w11 * dq.v[c])));
+            constexpr int dummy = 0; (void)dummy;
+            const int owner = d % L, k = d / L;  // compile-time after unrolling
+            unsigned i0 = ti[k][0], i1 = ti[k][1], i2 = ti[k][2], i3 = ti[k][3];
+            float w0 = tw[k][0], w1 = tw[k][1], w2 = tw[k][2], w3 = tw[k][3];
+            if constexpr (L > 1) {
+                i0 = __shfl_sync(0xffffffffu, i0, owner, L); i1 = __shfl_sync(0xffffffffu, i1, owner, L);
+                i2 = __shfl_sync(0xffffffffu, i2, owner, L); i3 = __shfl_sync(0xffffffffu, i3, owner, L);
+                w0 = __shfl_sync(0xffffffffu, w0, owner, L); w1 = __shfl_sync(0xffffffffu, w1, owner, L);
+                w2 = __shfl_sync(0xffffffffu, w2, owner, L); w3 = __shfl_sync(0xffffffffu, w3, owner, L);
             }
+            // texel index < 2^31 / C (checked on the host): one IMAD.WIDE.U32 per address
+            const P8 t00 = load_pairs<T>(srcp + (size_t)i0 * TB), t01 = load_pairs<T>(srcp + (size_t)i1 * TB);
+            const P8 t10 = load_pairs<T>(srcp + (size_t)i2 * TB), t11 = load_pairs<T>(srcp + (size_t)i3 * TB);
+            float cg[GPL];
+            blend_correlate<CPG>(t00, t01, t10, t11, w0, w1, w2, w3, rf, cg);
             float s = 0.0f;
 #pragma unroll
-            for (int g = 0; g < GPL; ++g) {
-                float cg = 0.0f;
-#pragma unroll
-                for (int c = 0; c < CPG; ++c) cg = fmaf(rf.v[g * CPG + c], wv[g * CPG + c], cg);
-                cor[g][d] = cg;
-                s += cg;
-            }
+            for (int g = 0; g < GPL; ++g) { cor[g][d] = cg[g]; s += cg[g]; }
             score[d] = s;
         }
-        // sum over all G groups: reduce across the L lanes of this pixel (reference cor_feat.sum(1), :1083)
+        // sum over all G groups = over the L lanes of the pixel (reference cor_feat.sum(1), :1083)
 #pragma unroll
         for (int m = 1; m < L; m <<= 1) {
 #pragma unroll
             for (int d = 0; d < D; ++d) score[d] += __shfl_xor_sync(0xffffffffu, score[d], m);
         }
-        // softmax over D of score / attn_temp, then / sqrt(C)
         float mx = score[0];
 #pragma unroll
         for (int d = 1; d < D; ++d) mx = fmaxf(mx, score[d]);
-        float e[D];
-        float es = 0.0f;
+        float e[D], es = 0.0f;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            e[d] = exp2f((score[d] - mx) * p.score_scale);
+            e[d] = ex2_approx((score[d] - mx) * p.score_scale);
             es += e[d];
         }
         const float norm = __fdividef(p.inv_sqrt_c, es);
@@ -149,61 +590,116 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) epi_fwd_kernel(const __g
     for (int d = 0; d < D; ++d) {
         const float inv = __frcp_rn(wsum[d]);
 #pragma unroll
-        for (int g = 0; g < GPL; ++g) {
-            const int gg = sub * GPL + g;
-            stg_stream(p.out + (((size_t)b * G + gg) * D + d) * plane + pix_off, acc[g][d] * inv);
-        }
+        for (int g = 0; g < GPL; ++g)
+            stg_stream(p.out + (((size_t)b * G + sub * GPL + g) * D + d) * plane + pix_off, acc[g][d] * inv);
         if (p.wsum != nullptr && sub == 0) p.wsum[((size_t)b * D + d) * plane + pix_off] = wsum[d];
     }
 }
 
 template <int C, int CPG, int D, typename T>
-static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
-    constexpr int PPW = 32 / (C / 8);
-    dim3 grid((p.W + PPW - 1) / PPW, (p.H + kWarpsPerCta - 1) / kWarpsPerCta, p.B);
+static int launch_direct(const EpiFwdParams& p, cudaStream_t stream) {
+    constexpr int L = C / 8, PPW = 32 / L, WX = L < 8 ? L : 8, TILE_W = PPW * WX, TILE_H = 8 / WX;
+    dim3 grid((p.W + TILE_W - 1) / TILE_W, (p.H + TILE_H - 1) / TILE_H, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
-    epi_fwd_kernel<C, CPG, D, T><<<grid, kWarpsPerCta * 32, 0, stream>>>(p);
+    epi_fwd_direct_kernel<C, CPG, D, T><<<grid, kThreads, MVSTER_MAX_SRC_VIEWS * 48, stream>>>(p);
     count_launch();
     MVSTER_CHECK_LAUNCH("epi_fwd launch");
     return MVSTER_OK;
 }
 
-template <int C, int CPG, typename T>
-static int dispatch_d(const EpiFwdParams& p, int D, cudaStream_t s) {
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+template <int C, int CPG, int D>
+static bool make_maps(EpiFwdParams& p, int Nsrc, int B, int Hs, int Ws) {
+    using S = Split<C, CPG, D>;
+    constexpr int TILE_H = S::TILE_H;
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Ws * C * 4, (cuuint64_t)Hs * Ws * C * 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TmaGeom<C>::BW, (cuuint32_t)(TILE_H + TmaGeom<C>::BH_EXTRA), 1};
+    const CUtensorMapSwizzle swz = (C == 8) ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+    for (int v = 0; v < Nsrc; ++v) {
+        CUresult r = enc(&p.tmap[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p.src[v]), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
+template <int C, int CPG, int D, bool TMA, typename T>
+static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
+    using S = Split<C, CPG, D>;
+    constexpr int TILE_H = S::TILE_H;
+    constexpr int TB = C * (int)sizeof(T);
+    const int smem = MVSTER_MAX_SRC_VIEWS * 48 +
+                     (TMA ? 2 * TmaGeom<C>::BW * (TILE_H + TmaGeom<C>::BH_EXTRA) * TB + 1024 + TmaGeom<C>::CTL_BYTES : 0);
+    static bool attr_set = false;  // per-function attribute, idempotent
+    if (smem > 48 * 1024 && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(epi_fwd_kernel<C, CPG, D, TMA, T>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return check_cuda(e, "epi_fwd: cudaFuncSetAttribute");
+        attr_set = true;
+    }
+    dim3 grid((p.W + S::TILE_W - 1) / S::TILE_W, (p.H + TILE_H - 1) / TILE_H, p.B);
+    if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
+    epi_fwd_kernel<C, CPG, D, TMA, T><<<grid, kThreads, smem, stream>>>(p);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("epi_fwd launch");
+    return MVSTER_OK;
+}
+
+template <int C, int CPG, int D>
+static int dispatch_variant(EpiFwdParams& p, int dtype, bool allow_tma, cudaStream_t s) {
+    if (dtype == MVSTER_BF16) return launch_direct<C, CPG, D, __nv_bfloat16>(p, s);
+    if constexpr (C == 8 || C == 16) {
+        // fine stages (32/64-byte fp32 texels): TMA-staged shared-memory gather when the tensor maps can be built
+        if (allow_tma && make_maps<C, CPG, D>(p, p.Nsrc, p.B, p.Hs, p.Ws)) return launch_fwd<C, CPG, D, true, float>(p, s);
+    }
+    return launch_direct<C, CPG, D, float>(p, s);
+}
+
+template <int C, int CPG>
+static int dispatch_d(EpiFwdParams& p, int D, int dtype, bool allow_tma, cudaStream_t s) {
     switch (D) {
-        case 4: return launch_fwd<C, CPG, 4, T>(p, s);
-        case 8: return launch_fwd<C, CPG, 8, T>(p, s);
+        case 4: return dispatch_variant<C, CPG, 4>(p, dtype, allow_tma, s);
+        case 8: return dispatch_variant<C, CPG, 8>(p, dtype, allow_tma, s);
         default: return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: D=%d not in {4,8}", D);
     }
 }
 
-template <int C, typename T>
-static int dispatch_cpg(const EpiFwdParams& p, int cpg, int D, cudaStream_t s) {
+template <int C>
+static int dispatch_cpg(EpiFwdParams& p, int cpg, int D, int dtype, bool allow_tma, cudaStream_t s) {
     switch (cpg) {
-        case 1: return dispatch_d<C, 1, T>(p, D, s);
-        case 2: return dispatch_d<C, 2, T>(p, D, s);
-        case 4: return dispatch_d<C, 4, T>(p, D, s);
-        case 8: return dispatch_d<C, 8, T>(p, D, s);
+        case 1: return dispatch_d<C, 1>(p, D, dtype, allow_tma, s);
+        case 2: return dispatch_d<C, 2>(p, D, dtype, allow_tma, s);
+        case 4: return dispatch_d<C, 4>(p, D, dtype, allow_tma, s);
+        case 8: return dispatch_d<C, 8>(p, D, dtype, allow_tma, s);
         default: return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: C/G=%d not in {1,2,4,8}", cpg);
     }
-}
-
-template <typename T>
-static int dispatch_c(const EpiFwdParams& p, int C, int cpg, int D, cudaStream_t s) {
-    switch (C) {
-        case 8: return dispatch_cpg<8, T>(p, cpg, D, s);
-        case 16: return dispatch_cpg<16, T>(p, cpg, D, s);
-        case 32: return dispatch_cpg<32, T>(p, cpg, D, s);
-        case 64: return dispatch_cpg<64, T>(p, cpg, D, s);
-        default: return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: C=%d not in {8,16,32,64}", C);
-    }
-}
-
-int epi_fwd_dispatch(const EpiFwdParams& p, int C, int G, int D, int dtype, cudaStream_t s) {
-    const int cpg = C / G;
-    if (dtype == MVSTER_F32) return dispatch_c<float>(p, C, cpg, D, s);
-    if (dtype == MVSTER_BF16) return dispatch_c<__nv_bfloat16>(p, C, cpg, D, s);
-    return fail(MVSTER_ERR_BAD_ARG, "epi_fwd: unknown dtype %d", dtype);
 }
 
 }  // namespace mvster
@@ -221,11 +717,12 @@ extern "C" int mvster_epi_fwd(const void* ref, const void* const* src, const flo
                     MVSTER_MAX_SRC_VIEWS);
     if (C % G != 0) return fail(MVSTER_ERR_BAD_ARG, "epi_fwd: C=%d not divisible by G=%d", C, G);
     if (!(attn_temp > 0.0f)) return fail(MVSTER_ERR_BAD_ARG, "epi_fwd: attn_temp must be > 0");
+    if (dtype != MVSTER_F32 && dtype != MVSTER_BF16) return fail(MVSTER_ERR_BAD_ARG, "epi_fwd: unknown dtype %d", dtype);
     if ((double)B * Hs * Ws * C >= 2147483648.0 || (double)H * W >= 2147483648.0)
         return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: tensor too large for 32-bit texel offsets");
     const uintptr_t align = (dtype == MVSTER_BF16) ? 16 : 32;
     if (((uintptr_t)ref) % align) return fail(MVSTER_ERR_ALIGN, "epi_fwd: ref not %d-byte aligned", (int)align);
-    EpiFwdParams p{};
+    static thread_local EpiFwdParams p;  // holds the 64-byte aligned tensor maps; one per calling thread
     p.ref = ref;
     for (int v = 0; v < Nsrc; ++v) {
         if (!src[v]) return fail(MVSTER_ERR_BAD_ARG, "epi_fwd: src[%d] is null", v);
@@ -240,5 +737,14 @@ extern "C" int mvster_epi_fwd(const void* ref, const void* const* src, const flo
     p.inv_sqrt_c = (float)(1.0 / sqrt((double)C));
     DeviceGuard guard(out);
     if (guard.status != MVSTER_OK) return guard.status;
-    return epi_fwd_dispatch(p, C, G, D, dtype, (cudaStream_t)stream);
+    const bool allow_tma = getenv("MVSTER_NO_TMA") == nullptr;
+    const int cpg = C / G;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (C) {
+        case 8: return dispatch_cpg<8>(p, cpg, D, dtype, allow_tma, s);
+        case 16: return dispatch_cpg<16>(p, cpg, D, dtype, allow_tma, s);
+        case 32: return dispatch_cpg<32>(p, cpg, D, dtype, allow_tma, s);
+        case 64: return dispatch_cpg<64>(p, cpg, D, dtype, allow_tma, s);
+        default: return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: C=%d not in {8,16,32,64}", C);
+    }
 }

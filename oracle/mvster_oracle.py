@@ -478,7 +478,7 @@ def cascade_port(features, projs, depth_values, logits, groups, ndepths, split_i
             inv = F.interpolate(inv.unsqueeze(1), [d, h, w], mode="trilinear", align_corners=True).squeeze(1)
             hypo = 1.0 / inv
         vol = epipolar_aggregate_port(features[s], projs[s], hypo, groups[s], attn_temp)
-        lg = logits[s]
+        lg = logits[s](hypo) if callable(logits[s]) else logits[s]   # stand-in for regnet(vol)
         idx = lg.max(1, keepdim=True)[1]                                                    # :1109-1113
         conf = torch.gather(lg, 1, idx).squeeze(1) / lg.sum(1)
         attn = F.softmax(lg, dim=1)                                                         # :1126
