@@ -31,6 +31,13 @@
 
 #include "common.cuh"
 
+#ifndef MVSTER_TMA_LD
+#define MVSTER_TMA_LD 1
+#endif
+#ifndef MVSTER_TMA_MINB
+#define MVSTER_TMA_MINB 2
+#endif
+
 namespace mvster {
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -40,12 +47,13 @@ template <int C, int CPG, int D>
 struct Split {
     static constexpr int CH = C;                           // channels per lane
     static constexpr int GPL = CH / CPG;                   // correlation groups per lane
-    static constexpr int DL = D;                           // hypotheses per lane
-    static constexpr int LC = 1, LD = 1, L = 1;            // lanes per pixel
-    static constexpr int PPW = 32;                         // pixels per warp
+    static constexpr int LD = MVSTER_TMA_LD;               // lanes splitting the hypotheses of a pixel
+    static constexpr int DL = D / LD;                      // hypotheses per lane
+    static constexpr int LC = 1, L = LD;                   // lanes per pixel
+    static constexpr int PPW = 32 / L;                     // pixels per warp
     static constexpr int NCHUNK = CH / 8;                  // 8-channel chunks per lane
-    static constexpr int WX = 1;                           // warps side by side in x (8 warps per CTA)
-    static constexpr int TILE_W = 32, TILE_H = 8;
+    static constexpr int WX = L;                           // warps side by side in x (8 warps per CTA)
+    static constexpr int TILE_W = 32, TILE_H = 8 / WX;
     static_assert(CH % 8 == 0 && 8 % CPG == 0, "a lane's 8-channel chunks must hold whole groups");
 };
 
@@ -181,7 +189,7 @@ __device__ __forceinline__ void blend_correlate(const P8& t00, const P8& t01, co
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C, int CPG, int D, bool TMA, typename T>
-__global__ void __launch_bounds__(kThreads, 2) epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
+__global__ void __launch_bounds__(kThreads, MVSTER_TMA_MINB) epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
     using S = Split<C, CPG, D>;
     constexpr int CH = S::CH, DL = S::DL, LC = S::LC, L = S::L, PPW = S::PPW, GPL = S::GPL, NCHUNK = S::NCHUNK;
     constexpr int G = C / CPG;

@@ -1,0 +1,186 @@
+#!/usr/bin/env python
+"""Secondary benchmarks (BASELINE.json configs 2, 4, 5 and per-stage K1 timings) - one JSON line each.
+
+    python scripts/bench_extra.py [--which stages,binpick,train,filter,ref_gpu] [--iters 20]
+
+  stages   per-stage K1 forward at the DTU 864x1152 N=5 shapes (B=8): time, algorithmic GB/s, roofline fraction
+  binpick  config 2: N=4 views 512x640, fused K1 forward, fp32 and bf16 features (B=8)
+  train    config 4 (single GPU part): K1 forward+backward at 512x640, B=2, N=5 through EpipolarAggregate
+  filter   config 5: 49 views 512x640, 9 sources each, fused geometric/photometric filter
+  ref_gpu  plain-PyTorch (eager, stock ATen kernels) restatement of the same op on the same GPU, as context
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import deep_reconstruction_with_epipolar_lines_mvster_b200 as mv  # noqa: E402
+from deep_reconstruction_with_epipolar_lines_mvster_b200 import ops, synthetic as syn  # noqa: E402
+
+HBM = 6547.2
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    HBM = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+
+
+def timed(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def smooth_hypo(b, d, h, w, stage, dev):
+    if stage == 0:
+        return mv.init_inverse_range(torch.from_numpy(syn.depth_values(b)).to(dev), d, None, None, h, w)
+    inv = torch.from_numpy(np.stack([1.0 / syn.smooth_depth_map(h // 2, w // 2, s, 560, 800) for s in range(b)])).to(dev)
+    half = 0.5 * (1 / 425.0 - 1 / 935.0) / 7 / (4.0 ** (stage - 1)) / (2 if stage > 1 else 1)
+    return mv.schedule_inverse_range(inv + half, inv - half, d, h, w)
+
+
+def stage_inputs(b, n, h0, w0, stage, dev, dtype=torch.float32):
+    c, g, d = syn.STAGE_CHANNELS[stage], syn.STAGE_GROUPS[stage], syn.STAGE_NDEPTHS[stage]
+    h, w = syn.stage_shape(h0, w0, stage)
+    gen = torch.Generator(device=dev).manual_seed(stage)
+    feats = []
+    for v in range(n):
+        x = torch.randn((b, c, h, w), device=dev, generator=gen) * 0.5
+        x = torch.nn.functional.avg_pool2d(x, 3, 1, 1, count_include_pad=False) * 1.7
+        feats.append(x.to(dtype).contiguous(memory_format=torch.channels_last))
+    proj = torch.from_numpy(syn.proj_matrices(b, n, h0, w0, stage, per_batch_jitter=0.02)).to(dev)
+    return feats, proj, smooth_hypo(b, d, h, w, stage, dev), g, d, c, h, w
+
+
+def k1_bytes(b, n, c, g, d, h, w, s):
+    return b * h * w * (n * c * s + d * 4 + g * d * 4)
+
+
+def bench_stages(args, dev):
+    for stage in range(4):
+        feats, proj, hypo, g, d, c, h, w = stage_inputs(8, 5, 864, 1152, stage, dev)
+        nhwc = [ops.to_nhwc(f) for f in feats]
+        rt = ops.compose_homographies(proj)
+        ms = timed(lambda: ops.epi_fwd(nhwc[0], nhwc[1:], rt, hypo, g, 2.0), args.iters)
+        by = k1_bytes(8, 5, c, g, d, h, w, 4)
+        print(json.dumps({"bench": "k1_fwd_stage%d" % (stage + 1), "shape": [8, 5, c, g, d, h, w], "ms": ms,
+                          "algorithmic_GB": by / 1e9, "GBps": by / ms / 1e6, "frac_hbm_roofline": by / ms / 1e6 / HBM}))
+
+
+def bench_binpick(args, dev):
+    for dtype, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        tot_ms, tot_by = 0.0, 0
+        for stage in range(4):
+            feats, proj, hypo, g, d, c, h, w = stage_inputs(8, 4, 512, 640, stage, dev, dtype)
+            nhwc = [ops.to_nhwc(f) for f in feats]
+            rt = ops.compose_homographies(proj)
+            tot_ms += timed(lambda: ops.epi_fwd(nhwc[0], nhwc[1:], rt, hypo, g, 2.0), args.iters)
+            tot_by += k1_bytes(8, 4, c, g, d, h, w, 2 if dtype == torch.bfloat16 else 4)
+        print(json.dumps({"bench": "binpick_k1_4stages_" + name, "config": "N=4 512x640 B=8", "ms_per_8_depth_maps": tot_ms,
+                          "depth_maps_per_s": 8e3 / tot_ms, "GBps": tot_by / tot_ms / 1e6,
+                          "frac_hbm_roofline": tot_by / tot_ms / 1e6 / HBM}))
+
+
+def bench_train(args, dev):
+    out = {}
+    for stage in (3, 2, 1, 0):
+        feats, proj, hypo, g, d, c, h, w = stage_inputs(2, 5, 512, 640, stage, dev)
+        feats = [f.requires_grad_(True) for f in feats]
+        gout = torch.randn((2, g, d, h, w), device=dev)
+
+        def step():
+            for f in feats:
+                f.grad = None
+            vol = mv.epipolar_aggregate(feats, proj, hypo, g, 2.0)
+            vol.backward(gout)
+
+        def fwd_only():
+            with torch.no_grad():
+                mv.epipolar_aggregate(feats, proj, hypo, g, 2.0)
+
+        out["stage%d_fwd_bwd_ms" % (stage + 1)] = timed(step, args.iters)
+        out["stage%d_fwd_ms" % (stage + 1)] = timed(fwd_only, args.iters)
+    out["bench"] = "train_k1_fwd_bwd"
+    out["config"] = "512x640 B=2 N=5 fp32, EpipolarAggregate autograd (includes layout views, zero-init of grads)"
+    print(json.dumps(out))
+
+
+def bench_filter(args, dev):
+    h, w, v, s = 512, 640, 49, 9
+    k = syn.intrinsics(h, w, 3)
+    es = [syn.grid_extrinsics(i, 7, 0.04) for i in range(v)]
+    # smooth analytic depths: rendering 49 views on the CPU is slow, use one rendered map per row of the rig
+    depths = syn.render_surface_depths(k, es, h, w, noise_mm=0.3, seed=0)
+    conf = np.random.RandomState(0).uniform(0, 1, size=(v, h, w)).astype(np.float32)
+    pairs = np.concatenate([np.arange(v)[:, None], syn.pair_list(v, s)], 1).astype(np.int32)
+    ks = np.stack([k] * v)
+    es = np.stack(es)
+    dz, cf = torch.from_numpy(depths).to(dev), torch.from_numpy(conf).to(dev)
+    cfg = mv.FilterConfig()
+    ms = timed(lambda: mv.filter_scene(dz, cf, ks, es, pairs, cfg), max(3, args.iters // 4))
+    photo, geo, final, avg, _ = mv.filter_scene(dz, cf, ks, es, pairs, cfg)
+    by = 441 * h * w * 4 + 49 * (2 * h * w * 4 + h * w * 4 + 3 * h * w)
+    line = {"bench": "filter_49x9_512x640", "ms_per_scene": ms, "scenes_per_s": 1e3 / ms, "pair_checks_per_s": 441e3 / ms,
+            "algorithmic_GB": by / 1e9, "GBps": by / ms / 1e6, "geo_mask_mean": float(geo.float().mean()),
+            "final_mask_mean": float(final.float().mean())}
+    if args.cpu_filter_pairs > 0:
+        from oracle import mvster_oracle as O
+        t0 = time.perf_counter()
+        n = 0
+        for r in range(v):
+            for j in range(s):
+                if n >= args.cpu_filter_pairs:
+                    break
+                src = int(pairs[r, 1 + j])
+                O.check_geometric_consistency_np(depths[r], ks[r], es[r], depths[src], ks[src], es[src], 1.0, 0.01, use_cv2=True)
+                n += 1
+        dt = time.perf_counter() - t0
+        line["cpu_port_ms_per_pair"] = 1e3 * dt / n
+        line["cpu_port_s_per_scene_extrapolated"] = dt / n * 441
+        line["cpu_pairs_timed"] = n
+    print(json.dumps(line))
+
+
+def bench_ref_gpu(args, dev):
+    """The reference's op sequence in eager PyTorch on the same GPU (stock ATen kernels), via the oracle port."""
+    from oracle import mvster_oracle as O
+    for stage in range(4):
+        feats, proj, hypo, g, d, c, h, w = stage_inputs(2, 5, 864, 1152, stage, dev)
+        feats = [f.contiguous() for f in feats]
+        with torch.no_grad():
+            ms = timed(lambda: O.epipolar_aggregate_port(feats, proj, hypo, g, 2.0), max(3, args.iters // 4))
+            nhwc = [ops.to_nhwc(f) for f in feats]
+            rt = ops.compose_homographies(proj)
+            ours = timed(lambda: ops.epi_fwd(nhwc[0], nhwc[1:], rt, hypo, g, 2.0), args.iters)
+        print(json.dumps({"bench": "eager_pytorch_vs_fused_stage%d" % (stage + 1), "shape": [2, 5, c, g, d, h, w],
+                          "eager_ms": ms, "fused_ms": ours, "speedup": ms / ours}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--cpu-filter-pairs", type=int, default=20)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    fns = {"stages": bench_stages, "binpick": bench_binpick, "train": bench_train, "filter": bench_filter,
+           "ref_gpu": bench_ref_gpu}
+    for name in args.which.split(","):
+        fns[name](args, dev)
+
+
+if __name__ == "__main__":
+    main()
