@@ -181,35 +181,47 @@ struct Taps {
     bool any;
 };
 
-// p = R*[x,y,1]*d + t ; z==0 -> 1e-9 ; (sx,sy) = p.xy / z        (reference models/mvs4net_utils.py:42-48)
-__device__ __forceinline__ Taps make_taps(float ax, float ay, float az, const Homography& h, float d, int Hs,
-                                          int Ws) {
-    float px = fmaf(ax, d, h.t0);
-    float py = fmaf(ay, d, h.t1);
+// Sample position of one hypothesis, clamped to [-1, Ws] x [-1, Hs].  A clamped coordinate has both of its taps
+// outside the image (or a zero weight on the one inside), so the sample contributes nothing - exactly like the
+// unclamped out-of-range sample under padding_mode='zeros' - while staying next to the image for the bounding box.
+// NaN collapses to -1 (the CPU reference samples nothing for NaN coordinates either).
+// p = R*[x,y,1]*d + t ; z==0 -> 1e-9 ; p.xy / z                                         (reference :42-48)
+__device__ __forceinline__ void sample_pos(float ax, float ay, float az, const Homography& h, float d, float wlim,
+                                           float hlim, float& sx, float& sy) {
+    const float px = fmaf(ax, d, h.t0);
+    const float py = fmaf(ay, d, h.t1);
     float pz = fmaf(az, d, h.t2);
     pz = (pz == 0.0f) ? 1e-9f : pz;
-    float sx = __fdiv_rn(px, pz);
-    float sy = __fdiv_rn(py, pz);
+    const float rz = fast_rcp(pz);
+    sx = fminf(fmaxf(px * rz, -1.0f), wlim);
+    sy = fminf(fmaxf(py * rz, -1.0f), hlim);
+}
+
+// Taps of one sample for the direct-gather kernels: clamped texel offsets and bounds-zeroed bilinear weights
+// (grid_sample padding_mode='zeros', align_corners=True; reference models/mvs4net_utils.py:59).
+__device__ __forceinline__ Taps make_taps(float ax, float ay, float az, const Homography& h, float d, int Hs,
+                                          int Ws) {
+    float sx, sy;
+    sample_pos(ax, ay, az, h, d, (float)Ws, (float)Hs, sx, sy);
+    const float x0f = floorf(sx), y0f = floorf(sy);
+    const float fx = sx - x0f, fy = sy - y0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;  // in [-1, Ws] x [-1, Hs] after the clamp
+    const bool vx0 = (unsigned)x0 < (unsigned)Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)Ws;
+    const bool vy0 = (unsigned)y0 < (unsigned)Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)Hs;
+    const int xc0 = min(max(x0, 0), Ws - 1), xc1 = min(x0 + 1, Ws - 1);
+    const int yc0 = min(max(y0, 0), Hs - 1), yc1 = min(y0 + 1, Hs - 1);
+    const float gx = vx0 ? 1.0f - fx : 0.0f, hx = vx1 ? fx : 0.0f;
+    const float gy = vy0 ? 1.0f - fy : 0.0f, hy = vy1 ? fy : 0.0f;
     Taps t;
-    // also false for NaN coordinates (the CPU reference samples nothing there)
-    t.any = (sx > -1.0f) && (sx < (float)Ws) && (sy > -1.0f) && (sy < (float)Hs);
-    float x0f = floorf(sx), y0f = floorf(sy);
-    float fx = sx - x0f, fy = sy - y0f;
-    int x0 = (int)x0f, y0 = (int)y0f;
-    bool vx0 = t.any && (x0 >= 0), vx1 = t.any && (x0 + 1 < Ws);
-    bool vy0 = (y0 >= 0), vy1 = (y0 + 1 < Hs);
-    int xc0 = max(x0, 0), xc1 = min(x0 + 1, Ws - 1);
-    int yc0 = max(y0, 0), yc1 = min(y0 + 1, Hs - 1);
-    if (!t.any) { xc0 = xc1 = yc0 = yc1 = 0; }
     t.o00 = yc0 * Ws + xc0;
     t.o01 = yc0 * Ws + xc1;
     t.o10 = yc1 * Ws + xc0;
     t.o11 = yc1 * Ws + xc1;
-    float gx = 1.0f - fx, gy = 1.0f - fy;
-    t.w00 = (vx0 && vy0) ? gx * gy : 0.0f;
-    t.w01 = (vx1 && vy0) ? fx * gy : 0.0f;
-    t.w10 = (vx0 && vy1) ? gx * fy : 0.0f;
-    t.w11 = (vx1 && vy1) ? fx * fy : 0.0f;
+    t.w00 = gx * gy;
+    t.w01 = hx * gy;
+    t.w10 = gx * hy;
+    t.w11 = hx * hy;
+    t.any = (t.w00 != 0.0f) || (t.w01 != 0.0f) || (t.w10 != 0.0f) || (t.w11 != 0.0f);
     return t;
 }
 

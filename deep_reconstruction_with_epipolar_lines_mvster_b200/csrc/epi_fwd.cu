@@ -141,22 +141,6 @@ __device__ __forceinline__ float group_sum(const f32x2 (&prod)[4], int g) {
     }
 }
 
-// Sample position of one hypothesis, clamped to [-1, Ws] x [-1, Hs].  A clamped coordinate has both of its taps
-// outside the image (or a zero weight on the one inside), so the sample contributes nothing - exactly like the
-// unclamped out-of-range sample under padding_mode='zeros' - while staying next to the image for the bounding box.
-// NaN collapses to -1 (the CPU reference samples nothing for NaN coordinates either).
-// p = R*[x,y,1]*d + t ; z==0 -> 1e-9 ; p.xy / z                                         (reference :42-48)
-__device__ __forceinline__ void sample_pos(float ax, float ay, float az, const Homography& h, float d, float wlim,
-                                           float hlim, float& sx, float& sy) {
-    const float px = fmaf(ax, d, h.t0);
-    const float py = fmaf(ay, d, h.t1);
-    float pz = fmaf(az, d, h.t2);
-    pz = (pz == 0.0f) ? 1e-9f : pz;
-    const float rz = fast_rcp(pz);
-    sx = fminf(fmaxf(px * rz, -1.0f), wlim);
-    sy = fminf(fmaxf(py * rz, -1.0f), hlim);
-}
-
 __device__ __forceinline__ Homography homography_from_smem(const float* rt_s) {
     const float4* hq = reinterpret_cast<const float4*>(rt_s);
     const float4 h0 = hq[0], h1 = hq[1], h2 = hq[2];

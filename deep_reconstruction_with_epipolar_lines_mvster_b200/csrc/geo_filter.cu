@@ -15,23 +15,21 @@
 
 namespace mvster {
 
-// Per-(ref, src) pair camera chain, float64:
-//   X_src  = A * ([x,y,1] * d_ref) + a          A = R_rel * K_ref^-1,      a = t_rel       (rel = E_src * E_ref^-1)
-//   q      = K_src * X_src
-//   X_ref' = Bm * ([u,v,1] * d_src) + bb        Bm = R_back * K_src^-1,    bb = t_back     (back = E_ref * E_src^-1)
-//   q'     = K_ref * X_ref'
+// Per-(ref, src) pair camera chain, float64, pre-composed on the host from the same inverses / products the
+// reference forms with np.linalg.inv / np.matmul (test_mvs4.py:619-647):
+//   q      = F * ([x,y,1] * d_ref) + f          F = K_src R_rel K_ref^-1,  f = K_src t_rel     (rel  = E_src E_ref^-1)
+//   (u,v)  = q.xy / q.z
+//   X_ref' = Bk * ([u,v,1] * d_src) + tb        Bk = R_back K_src^-1,      tb = t_back         (back = E_ref E_src^-1)
+//   q'     = G * ([u,v,1] * d_src) + g          G = K_ref Bk,              g = K_ref t_back
+// Only the z row of X_ref' is needed (depth_reprojected).
 struct PairCam {
-    double Kri[9];   // K_ref^-1
-    double Rrel[9];  // (E_src E_ref^-1)[:3,:3]
-    double trel[3];
-    double Ks[9];
-    double Ksi[9];   // K_src^-1
-    double Rback[9];
-    double tback[3];
-    double Kr[9];
+    double F[9], f[3];
+    double G[9], g[3];
+    double Bz[3], tbz;
     int src;  // source view index (into the depth stack), < 0 = skip
     int pad;
 };
+static_assert(sizeof(PairCam) % 8 == 0, "PairCam is copied as doubles");
 
 __device__ __forceinline__ void mat3_vec(const double* m, double x, double y, double z, double& ox, double& oy,
                                          double& oz) {
@@ -73,44 +71,40 @@ struct PairResult {
 };
 
 __device__ __forceinline__ PairResult check_pair(const PairCam& c, const float* __restrict__ depth_src, int H, int W,
-                                                 int x, int y, float d_ref, double pix_thr, float rel_thr) {
+                                                 int x, int y, float d_ref, double pix_thr2, float rel_thr) {
     PairResult r;
     const double dr = (double)d_ref;
     // step 1: reference pixel -> 3-D -> source pixel (:619-626)
-    double rx, ry, rz;
-    mat3_vec(c.Kri, (double)x * dr, (double)y * dr, dr, rx, ry, rz);
-    double sx, sy, sz;
-    mat3_vec(c.Rrel, rx, ry, rz, sx, sy, sz);
-    sx += c.trel[0]; sy += c.trel[1]; sz += c.trel[2];
     double qx, qy, qz;
-    mat3_vec(c.Ks, sx, sy, sz, qx, qy, qz);
-    const double u = qx / qz, v = qy / qz;
+    mat3_vec(c.F, (double)x * dr, (double)y * dr, dr, qx, qy, qz);
+    qx += c.f[0]; qy += c.f[1]; qz += c.f[2];
+    const double iq = 1.0 / qz;
+    const double u = qx * iq, v = qy * iq;
     r.x_src = (float)u;  // :630-631
     r.y_src = (float)v;
     // step 2: sample the source depth and project back (:632-647)
     const float ds = remap_linear(depth_src, H, W, r.x_src, r.y_src);
     const double dsd = (double)ds;
-    double bx, by, bz;
-    mat3_vec(c.Ksi, u * dsd, v * dsd, dsd, bx, by, bz);
-    double wx, wy, wz;
-    mat3_vec(c.Rback, bx, by, bz, wx, wy, wz);
-    wx += c.tback[0]; wy += c.tback[1]; wz += c.tback[2];
-    r.depth_reprojected = (float)wz;
+    const double ux = u * dsd, vx = v * dsd;
     double px, py, pz;
-    mat3_vec(c.Kr, wx, wy, wz, px, py, pz);
-    const float xr = (float)(px / pz), yr = (float)(py / pz);
-    // :661-667: dist is float64 (float32 maps minus int64 grids), the relative depth difference is float32
+    mat3_vec(c.G, ux, vx, dsd, px, py, pz);
+    px += c.g[0]; py += c.g[1]; pz += c.g[2];
+    r.depth_reprojected = (float)(c.Bz[0] * ux + c.Bz[1] * vx + c.Bz[2] * dsd + c.tbz);
+    const double ip = 1.0 / pz;
+    const float xr = (float)(px * ip), yr = (float)(py * ip);
+    // :661-667: dist is float64 (float32 maps minus int64 grids) - compared squared, sqrt is monotone; the relative
+    // depth difference is float32
     const double dx = (double)xr - (double)x, dy = (double)yr - (double)y;
-    const double dist = sqrt(dx * dx + dy * dy);
+    const double dist2 = dx * dx + dy * dy;
     const float rel = fabsf(r.depth_reprojected - d_ref) / d_ref;
-    r.mask = (dist < pix_thr) && (rel < rel_thr);
+    r.mask = (dist2 < pix_thr2) && (rel < rel_thr);
     return r;
 }
 
 __global__ void __launch_bounds__(256) geo_check_pair_kernel(const float* __restrict__ depth_ref,
                                                              const float* __restrict__ depth_src,
                                                              const __grid_constant__ PairCam cam,
-                                                             double pix_thr, float rel_thr,
+                                                             double pix_thr2, float rel_thr,
                                                              uint8_t* __restrict__ mask,
                                                              float* __restrict__ depth_rep, float* __restrict__ x2d,
                                                              float* __restrict__ y2d, int H, int W) {
@@ -119,7 +113,7 @@ __global__ void __launch_bounds__(256) geo_check_pair_kernel(const float* __rest
     if (x >= W || y >= H) return;
     // the 560-byte camera block is a kernel parameter: it sits in the constant bank and is read with uniform loads
     const size_t i = (size_t)y * W + x;
-    const PairResult r = check_pair(cam, depth_src, H, W, x, y, depth_ref[i], pix_thr, rel_thr);
+    const PairResult r = check_pair(cam, depth_src, H, W, x, y, depth_ref[i], pix_thr2, rel_thr);
     mask[i] = r.mask ? 1 : 0;
     depth_rep[i] = r.mask ? r.depth_reprojected : 0.0f;  // :668
     x2d[i] = r.x_src;
@@ -137,15 +131,22 @@ struct GeoFilterParams {
     float* depth_avg;
     int* geo_sum;
     int S, H, W;
-    double pix_thr;
+    double pix_thr2;
     float rel_thr, photo_thr;
     int geo_thr;
 };
 
 __global__ void __launch_bounds__(256) geo_filter_kernel(const GeoFilterParams p) {
+    extern __shared__ double cam_s[];  // the S camera blocks of this reference view: read as uniform LDS broadcasts
+    const int r = blockIdx.z;
+    {
+        const double* src = reinterpret_cast<const double*>(p.cams + (size_t)r * p.S);
+        const int n = p.S * (int)(sizeof(PairCam) / 8);
+        for (int i = threadIdx.x; i < n; i += 256) cam_s[i] = src[i];
+    }
+    __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int r = blockIdx.z;
     if (x >= p.W || y >= p.H) return;
     const size_t plane = (size_t)p.H * p.W;
     const size_t i = (size_t)y * p.W + x;
@@ -153,10 +154,11 @@ __global__ void __launch_bounds__(256) geo_filter_kernel(const GeoFilterParams p
     const float d_ref = p.depths[(size_t)ref * plane + i];
     int votes = 0;
     float sum = 0.0f;  // float32 running sum, like sum(list of float32 arrays) at :744
+    const PairCam* cams = reinterpret_cast<const PairCam*>(cam_s);
     for (int s = 0; s < p.S; ++s) {
-        const PairCam& c = p.cams[(size_t)r * p.S + s];
+        const PairCam& c = cams[s];
         if (c.src < 0) continue;
-        const PairResult pr = check_pair(c, p.depths + (size_t)c.src * plane, p.H, p.W, x, y, d_ref, p.pix_thr,
+        const PairResult pr = check_pair(c, p.depths + (size_t)c.src * plane, p.H, p.W, x, y, d_ref, p.pix_thr2,
                                          p.rel_thr);
         votes += pr.mask ? 1 : 0;
         sum = __fadd_rn(sum, pr.mask ? pr.depth_reprojected : 0.0f);
@@ -214,27 +216,49 @@ static void mul4(const double* a, const double* b, double* o) {
         }
 }
 
+static void mul3(const double* a, const double* b, double* o) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+}
+
 static void make_pair_cam(const double* Kr, const double* Er, const double* Ks, const double* Es, int src,
                           PairCam* c) {
-    double Eri[16], Esi[16], rel[16], back[16];
+    double Eri[16], Esi[16], rel[16], back[16], Kri[9], Ksi[9], Rrel[9], Rback[9], tmp[9], Bk[9];
     inv4(Er, Eri);
     inv4(Es, Esi);
     mul4(Es, Eri, rel);    // :622
     mul4(Er, Esi, back);   // :640
-    inv3(Kr, c->Kri);      // :619
-    inv3(Ks, c->Ksi);      // :637
+    inv3(Kr, Kri);         // :619
+    inv3(Ks, Ksi);         // :637
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { Rrel[i * 3 + j] = rel[i * 4 + j]; Rback[i * 3 + j] = back[i * 4 + j]; }
+    mul3(Rrel, Kri, tmp);
+    mul3(Ks, tmp, c->F);   // K_src R_rel K_ref^-1
+    mul3(Rback, Ksi, Bk);  // R_back K_src^-1
+    mul3(Kr, Bk, c->G);    // K_ref R_back K_src^-1
     for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) {
-            c->Rrel[i * 3 + j] = rel[i * 4 + j];
-            c->Rback[i * 3 + j] = back[i * 4 + j];
-            c->Ks[i * 3 + j] = Ks[i * 3 + j];
-            c->Kr[i * 3 + j] = Kr[i * 3 + j];
-        }
-        c->trel[i] = rel[i * 4 + 3];
-        c->tback[i] = back[i * 4 + 3];
+        c->f[i] = Ks[i * 3] * rel[3] + Ks[i * 3 + 1] * rel[7] + Ks[i * 3 + 2] * rel[11];
+        c->g[i] = Kr[i * 3] * back[3] + Kr[i * 3 + 1] * back[7] + Kr[i * 3 + 2] * back[11];
+        c->Bz[i] = Bk[6 + i];
     }
+    c->tbz = back[11];
     c->src = src;
     c->pad = 0;
+}
+
+// The camera blocks are staged through the stream-ordered allocator.  Its default pool gives memory back to the
+// driver at every synchronisation (release threshold 0), which turns each call into a fresh allocation; keep a few
+// MB cached instead.  Only users of cudaMallocAsync on this device are affected.
+static void keep_async_pool_warm(int dev) {
+    static bool done[64] = {false};
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t threshold = 64ull << 20;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+    done[dev] = true;
 }
 
 }  // namespace mvster
@@ -258,7 +282,8 @@ extern "C" int mvster_geo_check_pair(const float* depth_ref, const double* K_ref
     dim3 grid((W + 31) / 32, (H + 7) / 8);
     // NumPy compares the float64 pixel distance with a Python float (float64) and the float32 relative depth
     // difference with the same scalar cast to float32
-    geo_check_pair_kernel<<<grid, 256, 0, s>>>(depth_ref, depth_src, cam, condmask_pixel, (float)condmask_depth, mask,
+    geo_check_pair_kernel<<<grid, 256, 0, s>>>(depth_ref, depth_src, cam, condmask_pixel * condmask_pixel,
+                                               (float)condmask_depth, mask,
                                                depth_reprojected, x2d_src, y2d_src, H, W);
     count_launch();
     MVSTER_CHECK_LAUNCH("geo_check_pair launch");
@@ -293,6 +318,7 @@ extern "C" int mvster_geo_filter(const float* depths, const float* confs, const 
         }
     }
     const size_t cam_bytes = cams.size() * sizeof(PairCam), ref_bytes = refs.size() * sizeof(int);
+    keep_async_pool_warm(guard.dev);
     char* dev = nullptr;
     cudaError_t e = cudaMallocAsync(&dev, cam_bytes + ref_bytes, s);
     if (e != cudaSuccess) return check_cuda(e, "geo_filter: cudaMallocAsync");
@@ -300,10 +326,12 @@ extern "C" int mvster_geo_filter(const float* depths, const float* confs, const 
     if (e == cudaSuccess) e = cudaMemcpyAsync(dev + cam_bytes, refs.data(), ref_bytes, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { cudaFreeAsync(dev, s); return check_cuda(e, "geo_filter: H2D"); }
     GeoFilterParams p{depths, confs, reinterpret_cast<const PairCam*>(dev), reinterpret_cast<const int*>(dev + cam_bytes),
-                      photo, geo, final_mask, depth_avg, geo_sum, Sa, H, W, condmask_pixel, (float)condmask_depth,
+                      photo, geo, final_mask, depth_avg, geo_sum, Sa, H, W, condmask_pixel * condmask_pixel, (float)condmask_depth,
                       (float)photomask, geomask};
     dim3 grid((W + 31) / 32, (H + 7) / 8, R);
-    geo_filter_kernel<<<grid, 256, 0, s>>>(p);
+    const size_t cam_smem = (size_t)Sa * sizeof(PairCam);
+    if (cam_smem > 48 * 1024) { cudaFreeAsync(dev, s); return fail(MVSTER_ERR_UNSUPPORTED, "geo_filter: more than %d source views per reference view", (int)(48 * 1024 / sizeof(PairCam))); }
+    geo_filter_kernel<<<grid, 256, cam_smem, s>>>(p);
     count_launch();
     cudaError_t le = cudaGetLastError();
     cudaFreeAsync(dev, s);

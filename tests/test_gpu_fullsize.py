@@ -1,0 +1,129 @@
+"""Full-size (BASELINE.json shapes) checks of the CUDA path: windows of the 864x1152 problem against the float64
+oracle, and size-independent properties (view-permutation invariance, batch independence, partition of unity of the
+attention, idempotence of the filter under identical cameras).  Run on a B200 with ``-m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import deep_reconstruction_with_epipolar_lines_mvster_b200 as mv
+from deep_reconstruction_with_epipolar_lines_mvster_b200 import ops, synthetic as syn
+from oracle import mvster_oracle as O
+
+DEV = "cuda"
+H0, W0, N = 864, 1152, 5
+
+
+def _stage(stage, batch=1, seed=0):
+    c, g, d = syn.STAGE_CHANNELS[stage], syn.STAGE_GROUPS[stage], syn.STAGE_NDEPTHS[stage]
+    h, w = syn.stage_shape(H0, W0, stage)
+    feats = [syn.smooth_features(batch, c, h, w, 31 * stage + v + seed) for v in range(N)]
+    proj = syn.proj_matrices(batch, N, H0, W0, stage, per_batch_jitter=0.1)
+    if stage == 0:
+        hypo = O.init_inverse_range_np(syn.depth_values(batch), d, h, w)
+    else:
+        inv = 1.0 / np.stack([syn.smooth_depth_map(h // 2, w // 2, s + seed, 560, 800) for s in range(batch)])
+        half = np.float32(0.5 * (1 / 425.0 - 1 / 935.0) / 7 / 4.0 ** (stage - 1))
+        hypo = O.schedule_inverse_range_np((inv + half).astype(np.float32), (inv - half).astype(np.float32), d, h, w)
+    return feats, proj, hypo, g, d, h, w
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2, 3])
+def test_k1_full_size_windows_match_oracle(stage):
+    feats, proj, hypo, g, d, h, w = _stage(stage)
+    vol, wts = mv.epipolar_weights([f.to(DEV) for f in feats], torch.from_numpy(proj).to(DEV),
+                                   torch.from_numpy(hypo).to(DEV), g, 2.0)
+    vol, wts = vol.cpu().numpy(), wts.cpu().numpy()
+    assert np.isfinite(vol).all()
+    # partition of unity: per view the weights sum to 1/sqrt(C) over D
+    c = feats[0].shape[1]
+    assert np.abs(wts.sum(2) - 1.0 / np.sqrt(c)).max() < 1e-5
+    wh, ww = min(12, h), min(20, w)
+    for (y0, x0) in [(0, 0), (h - wh, w - ww), (h // 2 - wh // 2, w // 3), (h - wh, 0)]:
+        win = (y0, y0 + wh, x0, x0 + ww)
+        ref64, w64, _ = O.epipolar_aggregate_np(feats[0].numpy(), [f.numpy() for f in feats[1:]], proj, hypo, g, 2.0,
+                                                window=win)
+        assert np.abs(vol[:, :, :, y0:y0 + wh, x0:x0 + ww] - ref64).max() < 1e-4, (stage, win)
+        assert np.abs(wts[:, :, :, y0:y0 + wh, x0:x0 + ww] - w64).max() < 1e-4, (stage, win)
+
+
+@pytest.mark.parametrize("stage", [1, 3])
+def test_k1_view_permutation_and_batch_independence(stage):
+    feats, proj, hypo, g, d, h, w = _stage(stage, batch=2, seed=5)
+    dfe = [f.to(DEV) for f in feats]
+    dproj, dhyp = torch.from_numpy(proj).to(DEV), torch.from_numpy(hypo).to(DEV)
+    vol = mv.epipolar_aggregate(dfe, dproj, dhyp, g, 2.0)
+    # source views are summed: any order gives the same volume up to fp32 summation order
+    perm = [0, 3, 1, 4, 2]
+    vol_p = mv.epipolar_aggregate([dfe[i] for i in perm], dproj[:, perm].contiguous(), dhyp, g, 2.0)
+    assert (vol - vol_p).abs().max().item() < 2e-6
+    # batch items are independent: running item 1 alone is bit-identical
+    one = mv.epipolar_aggregate([f[1:2].contiguous() for f in dfe], dproj[1:2].contiguous(), dhyp[1:2].contiguous(), g, 2.0)
+    assert torch.equal(one[0], vol[1])
+
+
+def test_k1_large_footprint_falls_back_to_direct_gather():
+    """A 35 % scale change between the views makes every tile's footprint exceed the TMA box: the kernel must take
+    its per-view direct-gather path and still match the oracle."""
+    c, g, d, h, w = 8, 4, 4, 64, 96
+    feats = [syn.smooth_features(1, c, h, w, 77 + v) for v in range(3)]
+    proj = syn.proj_matrices(1, 3, h, w, 3)
+    proj[:, 1, 1, :2, :2] *= 1.35            # zoomed source camera
+    proj[:, 2, 1, :2, :2] *= 0.7
+    hypo = O.init_inverse_range_np(syn.depth_values(1), d, h, w)
+    vol = mv.epipolar_aggregate([f.to(DEV) for f in feats], torch.from_numpy(proj).to(DEV),
+                                torch.from_numpy(hypo).to(DEV), g, 2.0).cpu().numpy()
+    ref64, _, _ = O.epipolar_aggregate_np(feats[0].numpy(), [f.numpy() for f in feats[1:]], proj, hypo, g, 2.0)
+    assert np.abs(vol - ref64).max() < 1e-4
+
+
+def test_tail_and_schedule_full_size_vs_torch():
+    b, d, h, w = 2, 4, H0, W0
+    g = torch.Generator(device=DEV).manual_seed(0)
+    logits = torch.randn((b, d, h, w), device=DEV, generator=g) * 3
+    inv = torch.rand((b, h // 2, w // 2), device=DEV, generator=g) * 5e-4 + 1.2e-3
+    hypo = mv.schedule_inverse_range(inv + 3e-6, inv - 3e-6, d, h, w)
+    itv = torch.arange(d, device=DEV, dtype=torch.float32).reshape(1, -1, 1, 1) / (d - 1)
+    ref = (inv - 3e-6)[:, None] + ((inv + 3e-6) - (inv - 3e-6))[:, None] * itv
+    ref = 1.0 / torch.nn.functional.interpolate(ref.unsqueeze(1), [d, h, w], mode="trilinear", align_corners=True).squeeze(1)
+    assert ((hypo - ref).abs() / ref).max().item() < 1e-6
+    attn, depth, conf, lo, hi = ops.tail(logits, hypo, 1.0, True, True)
+    sm = torch.softmax(logits, 1)
+    assert (attn - sm).abs().max().item() < 1e-6
+    assert (attn.sum(1) - 1).abs().max().item() < 1e-5
+    idx = sm.max(1, keepdim=True)[1]
+    same = depth == torch.gather(hypo, 1, idx).squeeze(1)
+    assert same.float().mean().item() > 0.9999          # fp32 ties in the softmax only
+    mxl = logits.max(1)[0]
+    ok = logits.sum(1).abs() > 1e-2
+    assert torch.allclose(conf[ok], (mxl / logits.sum(1))[ok], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(lo - hi, 2.0 * (1.0 / hypo[:, 2] - 1.0 / hypo[:, 1]), rtol=1e-3, atol=1e-10)
+
+
+def test_filter_512x640_properties():
+    h, w, v = 512, 640, 6
+    k = syn.intrinsics(h, w, 3)
+    es = [syn.grid_extrinsics(i, 3, 0.05) for i in range(v)]
+    depths = syn.render_surface_depths(k, es, h, w, noise_mm=0.2, seed=3)
+    conf = np.random.RandomState(1).uniform(0, 1, size=(v, h, w)).astype(np.float32)
+    ks, es = np.stack([k] * v), np.stack(es)
+    pairs = np.concatenate([np.arange(v)[:, None], syn.pair_list(v, 4)], 1).astype(np.int32)
+    cfg = mv.FilterConfig()
+    photo, geo, final, avg, gsum = mv.filter_scene(depths, conf, ks, es, pairs, cfg, want_geo_sum=True)
+    assert torch.equal(final, photo & geo)
+    assert torch.equal(photo.cpu(), torch.from_numpy(conf > cfg.photomask))
+    assert geo.float().mean().item() > 0.9               # consistent synthetic surface
+    # source order does not matter for the vote count
+    pairs2 = pairs.copy()
+    pairs2[:, 1:] = pairs[:, :0:-1]
+    _, _, _, avg2, gsum2 = mv.filter_scene(depths, conf, ks, es, pairs2, cfg, want_geo_sum=True)
+    assert torch.equal(gsum, gsum2)
+    assert (avg - avg2).abs().max().item() < 1e-3
+    # one pair of the fused result against the per-pair entry point and the CPU oracle (1/32-px remap emulation)
+    r, s = int(pairs[2, 0]), int(pairs[2, 1])
+    m, drep, _, _ = mv.check_geometric_consistency(depths[r], ks[r], es[r], depths[s], ks[s], es[s], cfg)
+    mo, do, _, _ = O.check_geometric_consistency_np(depths[r], ks[r], es[r], depths[s], ks[s], es[s], 1.0, 0.01)
+    assert (m == mo).mean() >= 0.9999
+    both = m & mo
+    assert np.abs(drep[both] - do[both]).max() < 2e-3
