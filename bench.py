@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--views", type=int, default=5)
     ap.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32", help="feature storage type")
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the host-buffer leg (default min(steps,10))")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="issue the 16 launches of a step eagerly instead of replaying them as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scenes", type=int, default=2, help="timed scenes of the CPU baseline sample")
     return ap.parse_args()
@@ -288,20 +290,40 @@ def main():
     for _ in range(max(args.warmup, 3)):
         plan.run()
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    use_graph = args.graph
+    if use_graph:  # the 16 launches of a step replayed as one CUDA graph
+        try:
+            plan.capture()
+        except Exception as exc:  # capture is an optimisation: fall back to eager launches and say so in the line
+            print("[bench] CUDA graph capture failed (%s); eager launches" % exc, file=sys.stderr)
+            use_graph = False
     barrier()
     launches0 = _lib.launch_count()
     sampler.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for i in range(args.steps):
-        plan.stage_events = pairs[i]
-        plan.run(time_stage=dom)
+    if use_graph:
+        for i in range(args.steps):
+            plan.replay()
+    else:
+        for i in range(args.steps):
+            plan.stage_events = pairs[i]
+            plan.run(time_stage=dom)
     t_end.record()
     barrier()
     sampler.stop()
     plan.stage_events = None
     launches = _lib.launch_count() - launches0
     ms_total = t_start.elapsed_time(t_end)
+    if use_graph:
+        # a graph replay issues LAUNCHES_PER_RUN kernels without passing through the library's launch counter, and
+        # events cannot bracket a kernel inside it: the dominant kernel is timed in a separate eager pass
+        launches = args.steps * plan.LAUNCHES_PER_RUN
+        for p_ in pairs:
+            plan.stage_events = p_
+            plan.run(time_stage=dom)
+        torch.cuda.synchronize()
+        plan.stage_events = None
     k1_ms = statistics.mean(a.elapsed_time(b) for a, b in pairs)
 
     # ---- e2e leg: pinned host buffers in, depth + confidence out, every step ---------------------------------------
@@ -354,7 +376,7 @@ def main():
                     "h2d_bytes_per_step": plan.h2d_bytes(), "d2h_bytes_per_step": plan.d2h_bytes(),
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "CascadePlan.run_from_host (pinned host features/cameras in, depth+confidence out)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
             "roofline": {"kernel": "epi_fwd_kernel<C=8,CPG=2,D=4> (stage-4 K1 forward)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

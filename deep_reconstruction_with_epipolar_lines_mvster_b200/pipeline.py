@@ -107,6 +107,23 @@ class CascadePlan:
 
     LAUNCHES_PER_RUN = 16  # 4 stages x (schedule, compose, K1, tail)
 
+    # ---- CUDA graph: the 16 launches of one cascade as a single graph launch --------------------------------------
+    def capture(self):
+        """Capture ``run()`` into a CUDA graph (all buffers are pre-allocated and the kernels take raw pointers, so
+        the captured launches stay valid).  Only possible without a Python ``regnet`` callback."""
+        if self.regnet is not None:
+            raise RuntimeError("CascadePlan.capture(): a Python regnet callback cannot be captured")
+        self.run()  # warm-up outside capture: function attributes, TMA entry point, lazy module load
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.run()
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        return self.depth[-1], self.conf[-1]
+
     # ---- end to end from host memory -----------------------------------------------------------------------------------
     def make_host_buffers(self):
         """Pinned host mirrors of every per-step input, and pinned outputs for the final depth / confidence."""
