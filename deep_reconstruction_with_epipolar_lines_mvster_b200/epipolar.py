@@ -60,6 +60,21 @@ def epipolar_aggregate(features: Sequence[torch.Tensor], proj_matrices: torch.Te
                                    feature_dtype, *features[1:])
 
 
+def epipolar_aggregate_variant(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, depth_hypo: torch.Tensor,
+                               group_cor: bool, group_cor_dim: int, attn_fuse_d: bool, attn_temp: float) -> torch.Tensor:
+    """The reference's ``group_cor=False`` (variance cost, mvs4net_utils.py:1071) and/or ``attn_fuse_d=False``
+    (per-pixel weight, :1078-1081) options.  Forward only: no shipped configuration trains with them."""
+    if any(f.requires_grad for f in features) and torch.is_grad_enabled():
+        raise NotImplementedError("stagenet(B200): group_cor=False / attn_fuse_d=False have a fused forward kernel only; "
+                                  "run them under torch.no_grad() (every shipped training config uses the defaults)")
+    with torch.no_grad():
+        ref_n = ops.to_nhwc(features[0], torch.float32)
+        srcs_n = [ops.to_nhwc(s, torch.float32) for s in features[1:]]
+        rt = ops.compose_homographies(proj_matrices)
+        return ops.epi_fwd_mode(ref_n, srcs_n, rt, depth_hypo, int(group_cor_dim), float(attn_temp), bool(group_cor),
+                                bool(attn_fuse_d))
+
+
 def epipolar_weights(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, depth_hypo: torch.Tensor,
                      group_cor_dim: int, attn_temp: float, feature_dtype: Optional[torch.dtype] = None):
     """Volume plus the per-view attention weights ``[B,N-1,D,H,W]`` (the reference's ``cor_weight``,

@@ -132,6 +132,25 @@ def epi_fwd(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch
     return out, wsum, weights
 
 
+def epi_fwd_mode(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch.Tensor, hypo: torch.Tensor,
+                 groups: int, attn_temp: float, group_cor: bool, attn_fuse_d: bool) -> torch.Tensor:
+    """Forward of the reference's non-default options (variance cost / per-pixel weight); inference only."""
+    _require_cuda(ref_nhwc, "ref")
+    b, h, w, c = ref_nhwc.shape
+    nsrc = len(srcs_nhwc)
+    hs, ws = srcs_nhwc[0].shape[1:3]
+    hypo = _f32c(hypo, "depth_hypo")
+    d = hypo.shape[1]
+    if tuple(hypo.shape) != (b, d, h, w):
+        raise RuntimeError("depth_hypo must be [B,D,H,W]")
+    g = groups if group_cor else c
+    out = torch.empty((b, g, d, h, w), device=ref_nhwc.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_epi_fwd_mode(
+        _ptr(ref_nhwc), _ptr_array(srcs_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), b, nsrc, c, g, d, h, w, hs, ws,
+        float(attn_temp), _dtype_code(ref_nhwc), int(bool(group_cor)), int(bool(attn_fuse_d)), _stream(ref_nhwc)))
+    return out
+
+
 def epi_bwd(ref_nhwc, srcs_nhwc, rt, hypo, out, wsum, gout, groups: int, attn_temp: float
             ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """K1 backward.  Returns ``(grad_ref [B,H,W,C] fp32, [grad_src_v [B,Hs,Ws,C] fp32])``."""

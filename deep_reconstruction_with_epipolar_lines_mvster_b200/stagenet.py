@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .epipolar import EpipolarAggregate
+from .epipolar import EpipolarAggregate, epipolar_aggregate_variant
 
 
 class _Tail(torch.autograd.Function):
@@ -66,21 +66,17 @@ class stagenet(nn.Module):
 
     def forward(self, features, proj_matrices, depth_hypo, regnet, stage_idx, group_cor=False, group_cor_dim=8,
                 split_itv=1, fn=None):
-        if not group_cor:
-            raise NotImplementedError(
-                "stagenet(B200): group_cor=False (variance cost, reference mvs4net_utils.py:1071) has no fused kernel; "
-                "every shipped configuration uses group_cor=True")
-        if not self.attn_fuse_d:
-            raise NotImplementedError(
-                "stagenet(B200): attn_fuse_d=False (reference mvs4net_utils.py:1078-1081) has no fused kernel; "
-                "the reference default and every shipped configuration use attn_fuse_d=True")
         if self.vis_ETA:
             raise NotImplementedError("stagenet(B200): vis_ETA .npy dumps are a debugging aid of the reference and "
                                       "are not produced; use epipolar.epipolar_weights() for the attention weights")
         ref_feature = features[0]
         # steps 1-2: fused homography warp + group correlation + epipolar attention + view aggregation
-        cor_feats = EpipolarAggregate.apply(ref_feature, depth_hypo, proj_matrices, int(group_cor_dim),
-                                            float(self.attn_temp), self.feature_dtype, *features[1:])
+        if group_cor and self.attn_fuse_d:
+            cor_feats = EpipolarAggregate.apply(ref_feature, depth_hypo, proj_matrices, int(group_cor_dim),
+                                                float(self.attn_temp), self.feature_dtype, *features[1:])
+        else:  # variance cost (:1071) and / or per-pixel weight (:1078-1081): fused forward kernel, inference only
+            cor_feats = epipolar_aggregate_variant(features, proj_matrices, depth_hypo, bool(group_cor), int(group_cor_dim),
+                                                   bool(self.attn_fuse_d), float(self.attn_temp))
         # step 3: regularisation (unchanged, cuDNN)
         attn_weight = regnet(cor_feats)  # B D H W
         del cor_feats

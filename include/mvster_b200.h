@@ -73,11 +73,21 @@ int mvster_compose_homography_pair(const float* src_proj, const float* ref_proj,
  *   out      dev [B, G, D, H, W]   aggregated correlation volume (regnet input), fp32, written in full
  *   wsum     dev [B, D, H, W]      optional (NULL ok): 1e-8 + sum_v w_v, needed by the backward
  *   weights  dev [B, Nsrc, D, H, W] optional (NULL ok): per-view attention weights (reference `cor_weight`, :1083)
- * Supported: C in {8,16,32,64}, C/G in {1,2,4,8}, D in {4,8}; group_cor=True, attn_fuse_d=True (every shipped config).
+ * Supported: C in {8,16,32,64}, C/G in {1,2,4,8}, D in {4,8}; group_cor=True, attn_fuse_d=True (every shipped config;
+ * the other two combinations: mvster_epi_fwd_mode below).
  */
 int mvster_epi_fwd(const void* ref, const void* const* src, const float* rt, const float* hypo, float* out,
                    float* wsum, float* weights, int B, int Nsrc, int C, int G, int D, int H, int W, int Hs, int Ws,
                    float attn_temp, int dtype, void* stream);
+
+/* Same forward with the two reference options that no shipped configuration uses, forward only (inference):
+ *   group_cor = 0   : per-channel variance cost (ref - warped)^2, G must equal C  (models/mvs4net_utils.py:1071)
+ *   attn_fuse_d = 0 : one weight per pixel and view, max_D softmax_D(score), no temperature, no sqrt(C)
+ *                     (models/mvs4net_utils.py:1078-1081,1098)
+ * fp32 features only; group_cor = attn_fuse_d = 1 forwards to mvster_epi_fwd. */
+int mvster_epi_fwd_mode(const void* ref, const void* const* src, const float* rt, const float* hypo, float* out, int B,
+                        int Nsrc, int C, int G, int D, int H, int W, int Hs, int Ws, float attn_temp, int dtype,
+                        int group_cor, int attn_fuse_d, void* stream);
 
 /* ---- K1 backward -----------------------------------------------------------------------------------------
  * Replaces autograd through the same lines (grid_sampler_2d_backward, softmax_backward, ...).  Gradients flow to

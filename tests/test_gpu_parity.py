@@ -127,12 +127,9 @@ def test_k1_rejects_unsupported_configs(golden):
     g = golden("k1_stage4")
     feats = _features(g)
     proj, hypo = _cuda(g["proj"]), _cuda(g["hypo"])
-    net = mv.stagenet(inverse_depth=True, attn_temp=2.0)
+    # the variants have a forward kernel only: asking for gradients must fail loudly
     with pytest.raises(NotImplementedError):
-        net(feats, proj, hypo, lambda x: x.sum(1), 3, group_cor=False)
-    with pytest.raises(NotImplementedError):
-        mv.stagenet(inverse_depth=True, attn_fuse_d=False)(feats, proj, hypo, lambda x: x.sum(1), 3, group_cor=True,
-                                                           group_cor_dim=4)
+        mv.epipolar_aggregate_variant([f.clone().requires_grad_(True) for f in feats], proj, hypo, False, 8, True, 2.0)
     with pytest.raises(RuntimeError, match="not in"):
         bad = [torch.zeros(1, 24, 8, 8, device=DEV) for _ in range(2)]
         mv.epipolar_aggregate(bad, proj[:, :2], torch.ones(1, 4, 8, 8, device=DEV), 4, 2.0)
@@ -353,3 +350,61 @@ def test_filter_same_camera_is_identity():
     assert np.abs(d - depth).max() < 1e-3
     xs, ys = np.meshgrid(np.arange(w), np.arange(h))
     assert np.abs(x2 - xs).max() < 1e-3 and np.abs(y2 - ys).max() < 1e-3
+
+
+# --------------------------------------------------------------------------------------------------------------
+# re-entrancy: the reference's eval path wraps the model in nn.DataParallel (one host thread per GPU,
+# test_mvs4.py:393); the library keeps no global mutable state, so concurrent callers must not disturb each other
+# --------------------------------------------------------------------------------------------------------------
+def test_concurrent_host_threads_and_streams(golden):
+    import threading
+    cases = [golden(n) for n in ("k1_stage3", "k1_stage4", "k1_stage2", "k1_oob")]
+    results, errors = {}, []
+
+    def worker(i, g):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                feats = _features(g)
+                for _ in range(20):
+                    vol = mv.epipolar_aggregate(feats, _cuda(g["proj"]), _cuda(g["hypo"]), int(g["groups"]),
+                                                float(g["attn_temp"]))
+                stream.synchronize()
+            results[i] = np.abs(vol.cpu().numpy() - g["volume"]).max()
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i, g)) for i, g in enumerate(cases)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert all(v < 1e-4 for v in results.values()), results
+
+
+@pytest.mark.parametrize("group_cor,attn_fuse_d", [(False, True), (True, False), (False, False)])
+@pytest.mark.parametrize("name", ["k1_stage2", "k1_stage4", "k1_oob"])
+def test_k1_reference_option_variants(golden, name, group_cor, attn_fuse_d):
+    """group_cor=False (variance cost) and attn_fuse_d=False (per-pixel weight) against the float64 oracle, and through
+    the drop-in stagenet."""
+    g = golden(name)
+    feats = _features(g)
+    proj, hypo = _cuda(g["proj"]), _cuda(g["hypo"])
+    groups, temp = int(g["groups"]), float(g["attn_temp"])
+    srcs = [g["srcs"][:, v] for v in range(g["srcs"].shape[1])]
+    want, _, _ = O.epipolar_aggregate_np(g["ref"], srcs, g["proj"], g["hypo"], groups, temp, group_cor=group_cor,
+                                         attn_fuse_d=attn_fuse_d)
+    got = mv.epipolar_aggregate_variant(feats, proj, hypo, group_cor, groups, attn_fuse_d, temp)
+    assert got.shape == want.shape
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-4
+    net = mv.stagenet(inverse_depth=True, attn_fuse_d=attn_fuse_d, attn_temp=temp).eval()
+    seen = {}
+
+    def regnet(x):
+        seen["x"] = x
+        return x.sum(1)
+
+    with torch.no_grad():
+        net(feats, proj, hypo, regnet, 1, group_cor=group_cor, group_cor_dim=groups, split_itv=1.0)
+    assert torch.equal(seen["x"], got)
