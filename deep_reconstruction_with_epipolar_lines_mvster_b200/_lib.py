@@ -52,6 +52,15 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
+        path = os.environ.get("MVSTER_B200_LIB", LIB_PATH)  # experiments: an alternative build of the same ABI
+        if path != LIB_PATH:
+            lib = ctypes.CDLL(path)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+            return lib
         if not os.path.exists(LIB_PATH):
             if build_if_missing:
                 build_library()

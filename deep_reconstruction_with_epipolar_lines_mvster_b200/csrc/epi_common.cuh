@@ -9,7 +9,16 @@
 
 namespace mvster {
 
-constexpr int kWarps = 8;
+#ifndef MVSTER_DIRECT_WARPS
+#define MVSTER_DIRECT_WARPS 4   // warps per CTA of the direct-gather kernel
+#endif
+#ifndef MVSTER_DIRECT_MINB
+#define MVSTER_DIRECT_MINB 4
+#endif
+#ifndef MVSTER_DIRECT_WXMAX
+#define MVSTER_DIRECT_WXMAX 8   // at most this many warps side by side in x
+#endif
+constexpr int kWarps = MVSTER_DIRECT_WARPS;
 constexpr int kThreads = kWarps * 32;
 
 struct EpiFwdParams {
@@ -94,10 +103,11 @@ __device__ __forceinline__ void blend_correlate(const P8& t00, const P8& t01, co
 // lane group with width-L shuffles (8 values per sample).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C, int CPG, int D, typename T, bool VAR = false, bool FUSE_D = true>
-__global__ void __launch_bounds__(kThreads, 2) epi_fwd_direct_kernel(const __grid_constant__ EpiFwdParams p) {
+__global__ void __launch_bounds__(kThreads, MVSTER_DIRECT_MINB) epi_fwd_direct_kernel(const __grid_constant__ EpiFwdParams p) {
     constexpr int L = C / 8, PPW = 32 / L, GPL = 8 / CPG, G = C / CPG;
     constexpr int NOWN = (D + L - 1) / L;               // samples whose coordinates this lane computes
-    constexpr int WX = L < 8 ? L : 8, TILE_W = PPW * WX, TILE_H = 8 / WX;
+    constexpr int WXM = MVSTER_DIRECT_WXMAX < kWarps ? MVSTER_DIRECT_WXMAX : kWarps;
+    constexpr int WX = L < WXM ? L : WXM, TILE_W = PPW * WX, TILE_H = kWarps / WX;
     constexpr int TB = C * (int)sizeof(T);
     static_assert(L >= 1 && L <= 8 && 8 % CPG == 0, "C in {8,16,32,64}, C/G in {1,2,4,8}");
     static_assert(!VAR || CPG == 1, "the variance cost has one output channel per feature channel");
@@ -108,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 2) epi_fwd_direct_kernel(const __gri
     const int lane = tid & 31, warp = tid >> 5;
     const int pix = lane / L, sub = lane % L;
     const int b = blockIdx.z;
-    if (tid < p.Nsrc * 12) rt_s[tid] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + tid);
+    for (int i = tid; i < p.Nsrc * 12; i += kThreads) rt_s[i] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + i);
     int x = blockIdx.x * TILE_W + (warp % WX) * PPW + pix;
     int y = blockIdx.y * TILE_H + (warp / WX);
     const bool live = (x < p.W) && (y < p.H);
@@ -249,7 +259,8 @@ __global__ void __launch_bounds__(kThreads, 2) epi_fwd_direct_kernel(const __gri
 
 template <int C, int CPG, int D, typename T, bool VAR = false, bool FUSE_D = true>
 static int launch_direct(const EpiFwdParams& p, cudaStream_t stream) {
-    constexpr int L = C / 8, PPW = 32 / L, WX = L < 8 ? L : 8, TILE_W = PPW * WX, TILE_H = 8 / WX;
+    constexpr int WXM = MVSTER_DIRECT_WXMAX < kWarps ? MVSTER_DIRECT_WXMAX : kWarps;
+    constexpr int L = C / 8, PPW = 32 / L, WX = L < WXM ? L : WXM, TILE_W = PPW * WX, TILE_H = kWarps / WX;
     dim3 grid((p.W + TILE_W - 1) / TILE_W, (p.H + TILE_H - 1) / TILE_H, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
     epi_fwd_direct_kernel<C, CPG, D, T, VAR, FUSE_D><<<grid, kThreads, MVSTER_MAX_SRC_VIEWS * 48, stream>>>(p);

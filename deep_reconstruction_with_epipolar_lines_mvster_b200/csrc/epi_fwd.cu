@@ -33,7 +33,16 @@
 #define MVSTER_TMA_LD 1
 #endif
 #ifndef MVSTER_TMA_MINB
-#define MVSTER_TMA_MINB 2
+#define MVSTER_TMA_MINB 4
+#endif
+#ifndef MVSTER_TMA_WARPS
+#define MVSTER_TMA_WARPS 4
+#endif
+#ifndef MVSTER_TMA_BW
+#define MVSTER_TMA_BW 48
+#endif
+#ifndef MVSTER_TMA_BHX
+#define MVSTER_TMA_BHX 6
 #endif
 
 namespace mvster {
@@ -51,7 +60,7 @@ struct Split {
     static constexpr int PPW = 32 / L;                     // pixels per warp
     static constexpr int NCHUNK = CH / 8;                  // 8-channel chunks per lane
     static constexpr int WX = L;                           // warps side by side in x (8 warps per CTA)
-    static constexpr int TILE_W = 32, TILE_H = 8 / WX;
+    static constexpr int TILE_W = 32, TILE_H = MVSTER_TMA_WARPS / WX;
     static_assert(CH % 8 == 0 && 8 % CPG == 0, "a lane's 8-channel chunks must hold whole groups");
 };
 
@@ -61,9 +70,9 @@ struct TmaGeom {
     static constexpr int TB = C * 4;  // texel bytes (32 or 64)
     // staging box in texels; the width is a multiple of 8 so that the swizzle phase depends on x only.  Sized for
     // ~25 % scale change / a dozen texels of epipolar span across a tile; larger footprints take the direct path.
-    static constexpr int BW = 48;
+    static constexpr int BW = MVSTER_TMA_BW;
     static constexpr int CTL_BYTES = 16 /* 2 mbarriers */ + 48 /* 3 bbox slots */;
-    static constexpr int BH_EXTRA = 6;  // box height = tile height + BH_EXTRA
+    static constexpr int BH_EXTRA = MVSTER_TMA_BHX;  // box height = tile height + BH_EXTRA
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -102,7 +111,7 @@ __device__ __forceinline__ void lds_pairs(uint32_t addr, f32x2& a, f32x2& b) {
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C, int CPG, int D, bool TMA, typename T>
-__global__ void __launch_bounds__(kThreads, MVSTER_TMA_MINB) epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
+__global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
     using S = Split<C, CPG, D>;
     constexpr int CH = S::CH, DL = S::DL, LC = S::LC, L = S::L, PPW = S::PPW, GPL = S::GPL, NCHUNK = S::NCHUNK;
     constexpr int G = C / CPG;
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, MVSTER_TMA_MINB) epi_fwd_kernel(cons
     const int cl = lane % LC;         // channel chunk of this lane
     const int dl = (lane % L) / LC;   // hypothesis chunk of this lane
     const int b = blockIdx.z;
-    if (tid < p.Nsrc * 12) rt_s[tid] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + tid);
+    for (int i = tid; i < p.Nsrc * 12; i += MVSTER_TMA_WARPS * 32) rt_s[i] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + i);
     int x = blockIdx.x * S::TILE_W + (warp % WX) * PPW + pix;
     int y = blockIdx.y * TILE_H + (warp / WX);
     const bool live = (x < p.W) && (y < p.H);
@@ -428,7 +437,7 @@ static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
     }
     dim3 grid((p.W + S::TILE_W - 1) / S::TILE_W, (p.H + TILE_H - 1) / TILE_H, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
-    epi_fwd_kernel<C, CPG, D, TMA, T><<<grid, kThreads, smem, stream>>>(p);
+    epi_fwd_kernel<C, CPG, D, TMA, T><<<grid, MVSTER_TMA_WARPS * 32, smem, stream>>>(p);
     count_launch();
     MVSTER_CHECK_LAUNCH("epi_fwd launch");
     return MVSTER_OK;
