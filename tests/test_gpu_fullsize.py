@@ -127,3 +127,61 @@ def test_filter_512x640_properties():
     assert (m == mo).mean() >= 0.9999
     both = m & mo
     assert np.abs(drep[both] - do[both]).max() < 2e-3
+
+
+def test_k1_randomised_shapes_vs_oracle():
+    """Seeded sweep over ragged shapes (odd sizes, Hs != H, B > 1, every channel/group/depth combination the
+    library compiles) against the float64 oracle."""
+    rng = np.random.RandomState(123)
+    combos = [(8, 4, 4), (8, 8, 8), (8, 1, 4), (16, 4, 4), (16, 2, 8), (32, 8, 8), (32, 4, 4), (64, 8, 8), (64, 16, 4)]
+    for i, (c, g, d) in enumerate(combos):
+        b, n = int(rng.randint(1, 3)), int(rng.randint(2, 6))
+        h, w = int(rng.randint(5, 41)), int(rng.randint(7, 70))
+        hs, ws = (h, w) if i % 3 else (h + int(rng.randint(-3, 4)), w + int(rng.randint(-4, 5)))
+        feats = [syn.smooth_features(b, c, h, w, 1000 + i)]
+        feats += [syn.smooth_features(b, c, hs, ws, 2000 + 10 * i + v) for v in range(1, n)]
+        proj = syn.proj_matrices(b, n, h * 4, w * 4, 1, step_rad=float(rng.uniform(0.02, 0.2)),
+                                 per_batch_jitter=0.3, tilt_rad=float(rng.uniform(0, 0.05)))
+        lo = rng.uniform(430, 700)
+        hypo = np.sort(rng.uniform(lo, lo + 200, size=(b, d, h, w)).astype(np.float32), 1)[:, ::-1].copy()
+        vol, wts = mv.epipolar_weights([f.to(DEV) for f in feats], torch.from_numpy(proj).to(DEV),
+                                       torch.from_numpy(hypo).to(DEV), g, 1.7)
+        ref64, w64, _ = O.epipolar_aggregate_np(feats[0].numpy(), [f.numpy() for f in feats[1:]], proj, hypo, g, 1.7)
+        assert np.abs(vol.cpu().numpy() - ref64).max() < 1e-4, (c, g, d, b, n, h, w, hs, ws)
+        assert np.abs(wts.cpu().numpy() - w64).max() < 1e-4, (c, g, d, b, n, h, w, hs, ws)
+
+
+def test_cascade_free_running_vs_cpu_port():
+    """The whole 4-stage hot path (CascadePlan: schedule -> K1 -> stand-in regnet -> tail, stage after stage, nothing
+    teacher-forced) against the oracle's CPU port of the same cascade, at 128x192, N=4."""
+    from deep_reconstruction_with_epipolar_lines_mvster_b200.pipeline import CascadePlan
+    h0, w0, n = 128, 192, 4
+    plan = CascadePlan(1, n, h0, w0, device=DEV)
+    feats, projs, gts = [], [], []
+    for s in range(4):
+        h, w = syn.stage_shape(h0, w0, s)
+        fs = [syn.smooth_features(1, syn.STAGE_CHANNELS[s], h, w, 50 * s + v) for v in range(n)]
+        feats.append(fs)
+        projs.append(torch.from_numpy(syn.proj_matrices(1, n, h0, w0, s)))
+        gts.append(torch.from_numpy((1.0 / syn.smooth_depth_map(h, w, 9, 560, 800))[None].astype(np.float32)))
+        for v in range(n):
+            plan.features[s][v].copy_(fs[v].permute(0, 2, 3, 1))
+        plan.proj[s].copy_(projs[s])
+    dv = torch.from_numpy(syn.depth_values(1))
+    plan.depth_values.copy_(dv)
+
+    def logits_of(hypo, gt):   # deterministic stand-in for regnet: peaked at the hypothesis nearest the surface
+        inv = 1.0 / hypo
+        itv = (inv[:, 1:2] - inv[:, 0:1]).abs().clamp_min(1e-12)
+        return -4.0 * (inv - gt[:, None].to(hypo.device)).abs() / itv
+
+    plan.regnet = lambda s, vol: logits_of(plan.hypo[s], gts[s]).contiguous()
+    depth, conf = plan.run()
+    want_d, want_c = O.cascade_port(feats, projs, dv, [lambda hy, g=g: logits_of(hy, g) for g in gts],
+                                    syn.STAGE_GROUPS, syn.STAGE_NDEPTHS, syn.STAGE_SPLIT_ITV, 2.0)
+    depth, conf = depth.cpu(), conf.cpu()
+    # an arg-max flip anywhere in the cascade moves a pixel to a neighbouring hypothesis: allow a small fraction
+    close = (depth - want_d).abs() < 1e-3 * 2.5
+    assert close.float().mean().item() > 0.995, close.float().mean().item()
+    ok = close & torch.isfinite(want_c) & (want_c.abs() < 1e3)
+    assert torch.allclose(conf[ok], want_c[ok], rtol=1e-3, atol=1e-4)
