@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue the 16 launches of a step eagerly instead of replaying them as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-scenes", type=int, default=2, help="timed scenes of the CPU baseline sample")
+    ap.add_argument("--cpu-scenes", type=int, default=10, help="timed scenes of the CPU baseline sample")
     return ap.parse_args()
 
 

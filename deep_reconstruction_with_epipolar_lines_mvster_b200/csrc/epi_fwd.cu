@@ -38,6 +38,9 @@
 #ifndef MVSTER_TMA_WARPS
 #define MVSTER_TMA_WARPS 4
 #endif
+#ifndef MVSTER_CELL_REUSE
+#define MVSTER_CELL_REUSE 1
+#endif
 #ifndef MVSTER_TMA_BW
 #define MVSTER_TMA_BW 48
 #endif
@@ -262,6 +265,39 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
             if (v & 1) ++uses1; else ++uses0;
             const uint32_t buf = smem_base + (uint32_t)BUF_BYTES * (v & 1);
             constexpr uint32_t SWZ = (uint32_t)(TB / 16 - 1) << 4;  // swizzled chunk-index bits: [4] or [5:4]
+            if constexpr (NCHUNK == 1 && MVSTER_CELL_REUSE) {
+                // Consecutive hypotheses of a pixel are sub-texel to ~1 texel apart at the fine stages: when sample d
+                // falls into the same 2x2 texel cell as sample d-1 its taps are already in registers.  Neighbouring
+                // pixels change cell at the same hypothesis, so whole quarter-warps skip the LDS together.
+                P8 t00, t01, t10, t11;
+                int prx = INT_MIN, pry = INT_MIN;
+#pragma unroll
+                for (int d = 0; d < DL; ++d) {
+                    const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
+                    const float fx = sx[d] - x0f, fy = sy[d] - y0f;
+                    const int rx = (int)x0f - bx, ry = (int)y0f - by;
+                    if (d == 0 || rx != prx || ry != pry) {
+                        const uint32_t xo = (uint32_t)rx * TB;
+                        const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + xo;
+                        const uint32_t mA = (xo >> 3) & SWZ, mB = ((xo + TB) >> 3) & SWZ;
+                        const uint32_t aL = base ^ mA, aR = (base + TB) ^ mB;
+                        lds_pairs(aL, t00.q[0], t00.q[1]);
+                        lds_pairs(aL ^ 16u, t00.q[2], t00.q[3]);
+                        lds_pairs(aR, t01.q[0], t01.q[1]);
+                        lds_pairs(aR ^ 16u, t01.q[2], t01.q[3]);
+                        lds_pairs(aL + ROW_BYTES, t10.q[0], t10.q[1]);
+                        lds_pairs((aL ^ 16u) + ROW_BYTES, t10.q[2], t10.q[3]);
+                        lds_pairs(aR + ROW_BYTES, t11.q[0], t11.q[1]);
+                        lds_pairs((aR ^ 16u) + ROW_BYTES, t11.q[2], t11.q[3]);
+                    }
+                    prx = rx; pry = ry;
+                    const float gx = 1.0f - fx, gy = 1.0f - fy;
+                    float cg[8 / CPG];
+                    blend_correlate<CPG>(t00, t01, t10, t11, gx * gy, fx * gy, gx * fy, fx * fy, rf, cg);
+#pragma unroll
+                    for (int g = 0; g < 8 / CPG; ++g) cor[g][d] = cg[g];
+                }
+            } else {
 #pragma unroll
             for (int d = 0; d < DL; ++d) {
                 const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
@@ -291,6 +327,7 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
 #pragma unroll
                     for (int g = 0; g < 8 / CPG; ++g) cor[k * (8 / CPG) + g][d] = cg[g];
                 }
+            }
             }
         } else {
             // ---- direct gather from global memory, per-tap bounds weights --------------------------------------------
