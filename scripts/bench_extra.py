@@ -169,15 +169,44 @@ def bench_ref_gpu(args, dev):
                           "eager_ms": ms, "fused_ms": ours, "speedup": ms / ours}))
 
 
+def bench_ref_gpu_train(args, dev):
+    """Eager-PyTorch forward+backward of the reference op sequence vs the fused op, config-4 shape (512x640, B=2)."""
+    from oracle import mvster_oracle as O
+    for stage in (3, 2):
+        feats, proj, hypo, g, d, c, h, w = stage_inputs(2, 5, 512, 640, stage, dev)
+        gout = torch.randn((2, g, d, h, w), device=dev)
+        fe = [f.contiguous().requires_grad_(True) for f in feats]
+        ff = [f.requires_grad_(True) for f in feats]
+
+        def eager():
+            for f in fe:
+                f.grad = None
+            O.epipolar_aggregate_port(fe, proj, hypo, g, 2.0).backward(gout)
+
+        def fused():
+            for f in ff:
+                f.grad = None
+            mv.epipolar_aggregate(ff, proj, hypo, g, 2.0).backward(gout)
+
+        e_ms, f_ms = timed(eager, max(3, args.iters // 4)), timed(fused, args.iters)
+        torch.cuda.reset_peak_memory_stats()
+        eager(); torch.cuda.synchronize(); e_mem = torch.cuda.max_memory_allocated()
+        torch.cuda.reset_peak_memory_stats()
+        fused(); torch.cuda.synchronize(); f_mem = torch.cuda.max_memory_allocated()
+        print(json.dumps({"bench": "eager_pytorch_vs_fused_fwd_bwd_stage%d" % (stage + 1), "shape": [2, 5, c, g, d, h, w],
+                          "eager_ms": e_ms, "fused_ms": f_ms, "speedup": e_ms / f_ms,
+                          "eager_peak_MB": e_mem / 1e6, "fused_peak_MB": f_mem / 1e6}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu")
+    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--cpu-filter-pairs", type=int, default=20)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     fns = {"stages": bench_stages, "binpick": bench_binpick, "train": bench_train, "filter": bench_filter,
-           "ref_gpu": bench_ref_gpu}
+           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train}
     for name in args.which.split(","):
         fns[name](args, dev)
 
