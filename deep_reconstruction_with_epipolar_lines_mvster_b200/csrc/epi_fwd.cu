@@ -110,6 +110,47 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void lds_pairs(uint32_t addr, f32x2& a, f32x2& b) {
     asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
+// floor(s) as a float and as an int for |s| < 2^22 without the XU pipe (FRND / F2I are quarter-rate): adding 1.5*2^23
+// with round-toward-minus-infinity leaves floor(s) in the low mantissa bits.
+#ifndef MVSTER_FAST_FLOOR
+#define MVSTER_FAST_FLOOR 1
+#endif
+__device__ __forceinline__ void floor_fi(float s, float& f, int& i) {
+#if MVSTER_FAST_FLOOR
+    const float t = __fadd_rd(s, 12582912.0f);
+    f = t - 12582912.0f;
+    i = __float_as_int(t) - 0x4B400000;
+#else
+    f = floorf(s);
+    i = (int)f;
+#endif
+}
+__device__ __forceinline__ int floor_i(float s) {
+#if MVSTER_FAST_FLOOR
+    return __float_as_int(__fadd_rd(s, 12582912.0f)) - 0x4B400000;
+#else
+    return __float2int_rd(s);
+#endif
+}
+#ifndef MVSTER_BBOX_ATOM
+#define MVSTER_BBOX_ATOM 1
+#endif
+// CTA bounding box of the sample positions: ptxas turns a warp-uniform-address shared atomic into REDUX + one ATOMS
+__device__ __forceinline__ void bbox_update(int* slot, float lox, float loy, float hix, float hiy, int lane) {
+#if MVSTER_BBOX_ATOM
+    atomicMin(slot + 0, floor_i(lox)); atomicMin(slot + 1, floor_i(loy));
+    atomicMax(slot + 2, floor_i(hix)); atomicMax(slot + 3, floor_i(hiy));
+#else
+    const int wx0 = __reduce_min_sync(0xffffffffu, __float2int_rd(lox));
+    const int wy0 = __reduce_min_sync(0xffffffffu, __float2int_rd(loy));
+    const int wx1 = __reduce_max_sync(0xffffffffu, __float2int_rd(hix));
+    const int wy1 = __reduce_max_sync(0xffffffffu, __float2int_rd(hiy));
+    if (lane == 0) {
+        atomicMin(slot + 0, wx0); atomicMin(slot + 1, wy0);
+        atomicMax(slot + 2, wx1); atomicMax(slot + 3, wy1);
+    }
+#endif
+}
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
@@ -216,14 +257,7 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
             loy = fminf(loy, nsy[d]); hiy = fmaxf(hiy, nsy[d]);
         }
         const int slot = v % 3;
-        const int wx0 = __reduce_min_sync(0xffffffffu, __float2int_rd(lox));
-        const int wy0 = __reduce_min_sync(0xffffffffu, __float2int_rd(loy));
-        const int wx1 = __reduce_max_sync(0xffffffffu, __float2int_rd(hix));
-        const int wy1 = __reduce_max_sync(0xffffffffu, __float2int_rd(hiy));
-        if (lane == 0) {
-            atomicMin(&bbox[slot * 4 + 0], wx0); atomicMin(&bbox[slot * 4 + 1], wy0);
-            atomicMax(&bbox[slot * 4 + 2], wx1); atomicMax(&bbox[slot * 4 + 3], wy1);
-        }
+        bbox_update(&bbox[slot * 4], lox, loy, hix, hiy, lane);
         if (tid == 0) {  // recycle the slot that view v+1 will use (its last readers passed the previous barrier)
             const int nx = (v + 1) % 3;
             bbox[nx * 4 + 0] = INT_MAX; bbox[nx * 4 + 1] = INT_MAX;
@@ -273,9 +307,12 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
                 int prx = INT_MIN, pry = INT_MIN;
 #pragma unroll
                 for (int d = 0; d < DL; ++d) {
-                    const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
+                    float x0f, y0f;
+                    int x0i, y0i;
+                    floor_fi(sx[d], x0f, x0i);
+                    floor_fi(sy[d], y0f, y0i);
                     const float fx = sx[d] - x0f, fy = sy[d] - y0f;
-                    const int rx = (int)x0f - bx, ry = (int)y0f - by;
+                    const int rx = x0i - bx, ry = y0i - by;
                     if (d == 0 || rx != prx || ry != pry) {
                         const uint32_t xo = (uint32_t)rx * TB;
                         const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + xo;
@@ -300,9 +337,12 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
             } else {
 #pragma unroll
             for (int d = 0; d < DL; ++d) {
-                const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
+                float x0f, y0f;
+                int x0i, y0i;
+                floor_fi(sx[d], x0f, x0i);
+                floor_fi(sy[d], y0f, y0i);
                 const float fx = sx[d] - x0f, fy = sy[d] - y0f;
-                const int rx = (int)x0f - bx, ry = (int)y0f - by;
+                const int rx = x0i - bx, ry = y0i - by;
                 const uint32_t xo = (uint32_t)rx * TB;  // byte offset of the left texel inside its row
                 const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + xo;
                 // hardware swizzle: 16-byte chunk index ^= address bits [8:7] (64B mode) / [7] (32B mode); rows are a
@@ -416,6 +456,292 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// LINE kernel (fp32, C = 32: a texel is exactly one 128-byte line).  Through L1 a warp-wide gather of whole-line
+// texels costs ~2 cycles per extra line touched by one instruction (measured: L1 data pipe 73 % busy at 2.2x the
+// byte floor), shared memory costs 1 cycle per conflict-free 128 bytes.  So the coarse stage is staged by TMA as well:
+//   - a lane owns ALL channels of DL = D/4 hypotheses of a pixel (4 lanes per pixel): no redundant sample arithmetic,
+//     no tap broadcast shuffles;
+//   - a lane reads its texel in 16-byte chunks in the order (j + lane) & 7.  The 8 lanes of an LDS.128 phase then
+//     hit 8 different 16-byte bank groups WHATEVER texels they address (every texel starts on a 128-byte boundary,
+//     the box is not swizzled): the gather is conflict-free for arbitrary sample positions;
+//   - the reference channels and the accumulators live in the same rotated order; only the final store un-rotates.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef MVSTER_LINE_BW
+#define MVSTER_LINE_BW 40
+#endif
+#ifndef MVSTER_LINE_BHX
+#define MVSTER_LINE_BHX 4
+#endif
+#ifndef MVSTER_LINE_MINB
+#define MVSTER_LINE_MINB 2
+#endif
+struct LineGeom {
+    static constexpr int C = 32, TB = 128, LD = 4, PPW = 8, WARPS = 8, WX = 2, TILE_W = PPW * WX, TILE_H = WARPS / WX;
+    static constexpr int BW = MVSTER_LINE_BW, BH = TILE_H + MVSTER_LINE_BHX;
+    static constexpr int ROW_BYTES = BW * TB, BUF_BYTES = ROW_BYTES * BH;
+    static constexpr int CTL_BYTES = 16 + 48;
+    static constexpr int SMEM = 2 * BUF_BYTES + 1024 + CTL_BYTES + MVSTER_MAX_SRC_VIEWS * 48;
+};
+
+__device__ __forceinline__ void ldg128_pairs(const void* ptr, f32x2& a, f32x2& b) {
+    asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(ptr));
+}
+
+template <int CPG, int D>
+__global__ void __launch_bounds__(LineGeom::WARPS * 32, MVSTER_LINE_MINB) epi_fwd_line_kernel(const __grid_constant__ EpiFwdParams p) {
+    using Gm = LineGeom;
+    constexpr int C = Gm::C, TB = Gm::TB, LD = Gm::LD, DL = D / LD, G = C / CPG;
+    constexpr int GPC = 4 / CPG;  // correlation groups per 16-byte chunk
+    constexpr int NT = Gm::WARPS * 32;
+    static_assert(D % LD == 0 && (CPG == 1 || CPG == 2 || CPG == 4), "line kernel: D in {4,8}, C/G in {1,2,4}");
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ctl = smem_base + 2u * Gm::BUF_BYTES;
+    unsigned char* ctl_ptr = smem_raw + (ctl - smem_u32(smem_raw));
+    int* bbox = reinterpret_cast<int*>(ctl_ptr + 16);
+    float* rt_s = reinterpret_cast<float*>(ctl_ptr + Gm::CTL_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pix = lane / LD, dl = lane % LD;
+    const uint32_t rot = (uint32_t)lane & 7u;
+    const int b = blockIdx.z;
+    for (int i = tid; i < p.Nsrc * 12; i += NT) rt_s[i] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + i);
+    int x = blockIdx.x * Gm::TILE_W + (warp % Gm::WX) * Gm::PPW + pix;
+    int y = blockIdx.y * Gm::TILE_H + (warp / Gm::WX);
+    const bool live = (x < p.W) && (y < p.H);
+    x = min(x, p.W - 1);
+    y = min(y, p.H - 1);
+    if (tid == 0) {
+        mbar_init(ctl, 1);
+        mbar_init(ctl + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            bbox[i * 4 + 0] = INT_MAX; bbox[i * 4 + 1] = INT_MAX;
+            bbox[i * 4 + 2] = INT_MIN; bbox[i * 4 + 3] = INT_MIN;
+        }
+    }
+    __syncthreads();
+
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t pix_off = (size_t)y * p.W + x;
+
+    // reference channels in this lane's rotated chunk order, pre-scaled by 1/(C/G)
+    f32x2 rf[8][2];
+    {
+        const char* refp = reinterpret_cast<const char*>(p.ref) + ((size_t)b * plane + pix_off) * TB;
+        const f32x2 sc = pack2(1.0f / CPG, 1.0f / CPG);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            f32x2 a, c;
+            ldg128_pairs(refp + ((((uint32_t)j + rot) & 7u) << 4), a, c);
+            rf[j][0] = mul2(a, sc);
+            rf[j][1] = mul2(c, sc);
+        }
+    }
+    float hyp[DL];
+#pragma unroll
+    for (int d = 0; d < DL; ++d) hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + dl * DL + d) * plane + pix_off);
+
+    float acc[8 * GPC][DL], wsum[DL];
+#pragma unroll
+    for (int d = 0; d < DL; ++d) {
+        wsum[d] = 1e-8f;  // reference :1037
+#pragma unroll
+        for (int g = 0; g < 8 * GPC; ++g) acc[g][d] = 0.0f;
+    }
+    const float fxp = (float)x, fyp = (float)y;
+    const float wlim = (float)p.Ws, hlim = (float)p.Hs;
+
+    float nsx[DL], nsy[DL];
+    int nbx = 0, nby = 0;
+    bool nfit = false;
+    uint32_t uses0 = 0, uses1 = 0;
+
+    auto stage_view = [&](int v) {
+        const Homography h = homography_from_smem(rt_s + v * 12);
+        const float ax = fmaf(h.r00, fxp, fmaf(h.r01, fyp, h.r02));
+        const float ay = fmaf(h.r10, fxp, fmaf(h.r11, fyp, h.r12));
+        const float az = fmaf(h.r20, fxp, fmaf(h.r21, fyp, h.r22));
+#pragma unroll
+        for (int d = 0; d < DL; ++d) sample_pos(ax, ay, az, h, hyp[d], wlim, hlim, nsx[d], nsy[d]);
+        float lox = nsx[0], hix = nsx[0], loy = nsy[0], hiy = nsy[0];
+#pragma unroll
+        for (int d = 1; d < DL; ++d) {
+            lox = fminf(lox, nsx[d]); hix = fmaxf(hix, nsx[d]);
+            loy = fminf(loy, nsy[d]); hiy = fmaxf(hiy, nsy[d]);
+        }
+        const int slot = v % 3;
+        bbox_update(&bbox[slot * 4], lox, loy, hix, hiy, lane);
+        if (tid == 0) {
+            const int nx = (v + 1) % 3;
+            bbox[nx * 4 + 0] = INT_MAX; bbox[nx * 4 + 1] = INT_MAX;
+            bbox[nx * 4 + 2] = INT_MIN; bbox[nx * 4 + 3] = INT_MIN;
+        }
+        __syncthreads();
+        const int4 bb = *reinterpret_cast<const int4*>(&bbox[slot * 4]);
+        nbx = bb.x; nby = bb.y;
+        nfit = (bb.z - bb.x + 2 <= Gm::BW) && (bb.w - bb.y + 2 <= Gm::BH);
+        if (nfit && tid == 0) {
+            const uint32_t bar = ctl + 8u * (v & 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (uint32_t)Gm::BUF_BYTES);
+            tma_load_4d(smem_base + (uint32_t)Gm::BUF_BYTES * (v & 1), &p.tmap[v], bar, 0, nbx, nby, b);
+        }
+    };
+
+    // blend one 16-byte chunk of the four taps, multiply by the reference chunk, reduce to its groups
+    auto chunk_cor = [&](const f32x2 (&t)[4][2], const float (&w)[4], int j, float* cg) {
+        f32x2 wv0 = mul2(pack2(w[0], w[0]), t[0][0]), wv1 = mul2(pack2(w[0], w[0]), t[0][1]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const f32x2 pw = pack2(w[k], w[k]);
+            wv0 = fma2(pw, t[k][0], wv0);
+            wv1 = fma2(pw, t[k][1], wv1);
+        }
+        const f32x2 p0 = mul2(rf[j][0], wv0), p1 = mul2(rf[j][1], wv1);
+        float a0, a1, b0, b1;
+        if constexpr (CPG == 4) {
+            unpack2(add2(p0, p1), a0, a1);
+            cg[0] = a0 + a1;
+        } else if constexpr (CPG == 2) {
+            unpack2(p0, a0, a1); unpack2(p1, b0, b1);
+            cg[0] = a0 + a1; cg[1] = b0 + b1;
+        } else {
+            unpack2(p0, cg[0], cg[1]); unpack2(p1, cg[2], cg[3]);
+        }
+    };
+
+    stage_view(0);
+
+#pragma unroll 1
+    for (int v = 0; v < p.Nsrc; ++v) {
+        float sx[DL], sy[DL];
+#pragma unroll
+        for (int d = 0; d < DL; ++d) { sx[d] = nsx[d]; sy[d] = nsy[d]; }
+        const int bx = nbx, by = nby;
+        const bool fit = nfit;
+        if (v + 1 < p.Nsrc) stage_view(v + 1);
+
+        float cor[8 * GPC][DL];
+        if (fit) {
+            const uint32_t parity = ((v & 1) ? uses1 : uses0) & 1u;
+            mbar_wait(ctl + 8u * (v & 1), parity);
+            if (v & 1) ++uses1; else ++uses0;
+            const uint32_t buf = smem_base + (uint32_t)Gm::BUF_BYTES * (v & 1);
+#pragma unroll
+            for (int d = 0; d < DL; ++d) {
+                float x0f, y0f;
+                int x0i, y0i;
+                floor_fi(sx[d], x0f, x0i);
+                floor_fi(sy[d], y0f, y0i);
+                const float fx = sx[d] - x0f, fy = sy[d] - y0f;
+                const int rx = x0i - bx, ry = y0i - by;
+                const uint32_t base = buf + (uint32_t)ry * Gm::ROW_BYTES + (uint32_t)rx * TB;
+                const float gx = 1.0f - fx, gy = 1.0f - fy;
+                const float w[4] = {gx * gy, fx * gy, gx * fy, fx * fy};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t a = base + ((((uint32_t)j + rot) & 7u) << 4);
+                    f32x2 t[4][2];
+                    lds_pairs(a, t[0][0], t[0][1]);
+                    lds_pairs(a + TB, t[1][0], t[1][1]);
+                    lds_pairs(a + Gm::ROW_BYTES, t[2][0], t[2][1]);
+                    lds_pairs(a + Gm::ROW_BYTES + TB, t[3][0], t[3][1]);
+                    float cg[GPC];
+                    chunk_cor(t, w, j, cg);
+#pragma unroll
+                    for (int g = 0; g < GPC; ++g) cor[j * GPC + g][d] = cg[g];
+                }
+            }
+        } else {
+            // footprint larger than the box: direct gather (same rotated chunk order), per-tap bounds weights
+            const char* srcp = reinterpret_cast<const char*>(p.src[v]) + (size_t)b * p.Hs * p.Ws * TB;
+#pragma unroll
+            for (int d = 0; d < DL; ++d) {
+                const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
+                const float fx = sx[d] - x0f, fy = sy[d] - y0f;
+                const int x0 = (int)x0f, y0 = (int)y0f;
+                const bool vx0 = (unsigned)x0 < (unsigned)p.Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)p.Ws;
+                const bool vy0 = (unsigned)y0 < (unsigned)p.Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)p.Hs;
+                const int xc0 = min(max(x0, 0), p.Ws - 1), xc1 = min(x0 + 1, p.Ws - 1);
+                const int yc0 = min(max(y0, 0), p.Hs - 1), yc1 = min(y0 + 1, p.Hs - 1);
+                const float gx = vx0 ? 1.0f - fx : 0.0f, hx = vx1 ? fx : 0.0f;
+                const float gy = vy0 ? 1.0f - fy : 0.0f, hy = vy1 ? fy : 0.0f;
+                const float w[4] = {gx * gy, hx * gy, gx * hy, hx * hy};
+                const unsigned r0 = (unsigned)(yc0 * p.Ws), r1 = (unsigned)(yc1 * p.Ws);
+                const char* a00 = srcp + (size_t)(r0 + (unsigned)xc0) * TB;
+                const char* a01 = srcp + (size_t)(r0 + (unsigned)xc1) * TB;
+                const char* a10 = srcp + (size_t)(r1 + (unsigned)xc0) * TB;
+                const char* a11 = srcp + (size_t)(r1 + (unsigned)xc1) * TB;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t co = (((uint32_t)j + rot) & 7u) << 4;
+                    f32x2 t[4][2];
+                    ldg128_pairs(a00 + co, t[0][0], t[0][1]);
+                    ldg128_pairs(a01 + co, t[1][0], t[1][1]);
+                    ldg128_pairs(a10 + co, t[2][0], t[2][1]);
+                    ldg128_pairs(a11 + co, t[3][0], t[3][1]);
+                    float cg[GPC];
+                    chunk_cor(t, w, j, cg);
+#pragma unroll
+                    for (int g = 0; g < GPC; ++g) cor[j * GPC + g][d] = cg[g];
+                }
+            }
+        }
+
+        // score[d] = sum over all G groups (all lane-local); softmax over D crosses the LD hypothesis lanes
+        float score[DL];
+#pragma unroll
+        for (int d = 0; d < DL; ++d) {
+            float s0 = cor[0][d], s1 = cor[1][d];
+#pragma unroll
+            for (int g = 2; g < 8 * GPC; g += 2) { s0 += cor[g][d]; s1 += cor[g + 1][d]; }
+            score[d] = s0 + s1;
+        }
+        float mx = score[0];
+#pragma unroll
+        for (int d = 1; d < DL; ++d) mx = fmaxf(mx, score[d]);
+#pragma unroll
+        for (int m = 1; m < LD; m <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        float e[DL], es = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DL; ++d) {
+            e[d] = ex2_approx((score[d] - mx) * p.score_scale);
+            es += e[d];
+        }
+#pragma unroll
+        for (int m = 1; m < LD; m <<= 1) es += __shfl_xor_sync(0xffffffffu, es, m);
+        const float norm = __fdividef(p.inv_sqrt_c, es);
+#pragma unroll
+        for (int d = 0; d < DL; ++d) {
+            const float w = e[d] * norm;
+            wsum[d] += w;
+#pragma unroll
+            for (int g = 0; g < 8 * GPC; ++g) acc[g][d] = fmaf(w, cor[g][d], acc[g][d]);
+            if (p.weights != nullptr && live)
+                p.weights[(((size_t)b * p.Nsrc + v) * D + dl * DL + d) * plane + pix_off] = w;
+        }
+    }
+
+    if (!live) return;
+#pragma unroll
+    for (int d = 0; d < DL; ++d) {
+        const float inv = __frcp_rn(wsum[d]);
+        const int dd = dl * DL + d;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g0 = (int)(((uint32_t)j + rot) & 7u) * GPC;  // un-rotate: chunk -> first group of the chunk
+#pragma unroll
+            for (int g = 0; g < GPC; ++g)
+                stg_stream(p.out + (((size_t)b * G + g0 + g) * D + dd) * plane + pix_off, acc[j * GPC + g][d] * inv);
+        }
+        if (p.wsum != nullptr) p.wsum[((size_t)b * D + dd) * plane + pix_off] = wsum[d];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -480,12 +806,52 @@ static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
     return MVSTER_OK;
 }
 
+static bool make_line_maps(EpiFwdParams& p, int Nsrc, int B, int Hs, int Ws) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    constexpr int C = LineGeom::C;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Ws * C * 4, (cuuint64_t)Hs * Ws * C * 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)LineGeom::BW, (cuuint32_t)LineGeom::BH, 1};
+    for (int v = 0; v < Nsrc; ++v) {
+        CUresult r = enc(&p.tmap[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p.src[v]), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
+template <int CPG, int D>
+static int launch_line(const EpiFwdParams& p, cudaStream_t stream) {
+    using Gm = LineGeom;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(epi_fwd_line_kernel<CPG, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Gm::SMEM);
+        if (e != cudaSuccess) return check_cuda(e, "epi_fwd(line): cudaFuncSetAttribute");
+        attr_set = true;
+    }
+    dim3 grid((p.W + Gm::TILE_W - 1) / Gm::TILE_W, (p.H + Gm::TILE_H - 1) / Gm::TILE_H, p.B);
+    if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
+    epi_fwd_line_kernel<CPG, D><<<grid, Gm::WARPS * 32, Gm::SMEM, stream>>>(p);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("epi_fwd(line) launch");
+    return MVSTER_OK;
+}
+
 template <int C, int CPG, int D>
 static int dispatch_variant(EpiFwdParams& p, int dtype, bool allow_tma, cudaStream_t s) {
     if (dtype == MVSTER_BF16) return launch_direct<C, CPG, D, __nv_bfloat16>(p, s);
     if constexpr (C == 8 || C == 16) {
         // fine stages (32/64-byte fp32 texels): TMA-staged shared-memory gather when the tensor maps can be built
         if (allow_tma && make_maps<C, CPG, D>(p, p.Nsrc, p.B, p.Hs, p.Ws)) return launch_fwd<C, CPG, D, true, float>(p, s);
+    }
+    if constexpr (C == 32 && CPG <= 4) {
+        // whole-line texels: conflict-free rotated shared-memory gather (see epi_fwd_line_kernel)
+        if (allow_tma && getenv("MVSTER_NO_LINE") == nullptr && make_line_maps(p, p.Nsrc, p.B, p.Hs, p.Ws))
+            return launch_line<CPG, D>(p, s);
     }
     return launch_direct<C, CPG, D, float>(p, s);
 }

@@ -63,10 +63,11 @@ def test_k1_view_permutation_and_batch_independence(stage):
     assert torch.equal(one[0], vol[1])
 
 
-def test_k1_large_footprint_falls_back_to_direct_gather():
+@pytest.mark.parametrize("c,g,d", [(8, 4, 4), (16, 4, 4), (32, 8, 8), (32, 16, 4)])
+def test_k1_large_footprint_falls_back_to_direct_gather(c, g, d):
     """A 35 % scale change between the views makes every tile's footprint exceed the TMA box: the kernel must take
-    its per-view direct-gather path and still match the oracle."""
-    c, g, d, h, w = 8, 4, 4, 64, 96
+    its per-view direct-gather path and still match the oracle (swizzled-box kernels C=8/16 and the line kernel C=32)."""
+    h, w = 64, 96
     feats = [syn.smooth_features(1, c, h, w, 77 + v) for v in range(3)]
     proj = syn.proj_matrices(1, 3, h, w, 3)
     proj[:, 1, 1, :2, :2] *= 1.35            # zoomed source camera
@@ -133,7 +134,8 @@ def test_k1_randomised_shapes_vs_oracle():
     """Seeded sweep over ragged shapes (odd sizes, Hs != H, B > 1, every channel/group/depth combination the
     library compiles) against the float64 oracle."""
     rng = np.random.RandomState(123)
-    combos = [(8, 4, 4), (8, 8, 8), (8, 1, 4), (16, 4, 4), (16, 2, 8), (32, 8, 8), (32, 4, 4), (64, 8, 8), (64, 16, 4)]
+    combos = [(8, 4, 4), (8, 8, 8), (8, 1, 4), (16, 4, 4), (16, 2, 8), (32, 8, 8), (32, 4, 4), (32, 16, 8), (32, 32, 4),
+              (64, 8, 8), (64, 16, 4)]
     for i, (c, g, d) in enumerate(combos):
         b, n = int(rng.randint(1, 3)), int(rng.randint(2, 6))
         h, w = int(rng.randint(5, 41)), int(rng.randint(7, 70))
@@ -149,6 +151,19 @@ def test_k1_randomised_shapes_vs_oracle():
         ref64, w64, _ = O.epipolar_aggregate_np(feats[0].numpy(), [f.numpy() for f in feats[1:]], proj, hypo, g, 1.7)
         assert np.abs(vol.cpu().numpy() - ref64).max() < 1e-4, (c, g, d, b, n, h, w, hs, ws)
         assert np.abs(wts.cpu().numpy() - w64).max() < 1e-4, (c, g, d, b, n, h, w, hs, ws)
+
+
+def test_k1_line_kernel_equals_direct_kernel(monkeypatch):
+    """C=32 (whole-line texels): the TMA-staged rotated-chunk kernel and the direct-gather kernel (MVSTER_NO_LINE=1)
+    compute the same sums in a different order - they must agree to fp32 rounding at the full stage-2 size."""
+    feats, proj, hypo, g, d, h, w = _stage(1, batch=2, seed=3)
+    dfe = [f.to(DEV) for f in feats]
+    dproj, dhyp = torch.from_numpy(proj).to(DEV), torch.from_numpy(hypo).to(DEV)
+    vol, wts = mv.epipolar_weights(dfe, dproj, dhyp, g, 2.0)
+    monkeypatch.setenv("MVSTER_NO_LINE", "1")
+    vol_d, wts_d = mv.epipolar_weights(dfe, dproj, dhyp, g, 2.0)
+    assert (vol - vol_d).abs().max().item() < 5e-6
+    assert (wts - wts_d).abs().max().item() < 5e-6
 
 
 def test_cascade_free_running_vs_cpu_port():
