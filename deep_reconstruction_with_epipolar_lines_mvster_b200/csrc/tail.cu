@@ -1,7 +1,7 @@
 // K2a: depth / confidence tail of stagenet.forward (models/mvs4net_utils.py:1109-1156) as one streaming kernel,
 // and the hypothesis schedule (models/mvs4net_utils.py:79-94).  All HBM-bound elementwise work over [B,D,H,W]:
 // one thread per pixel, D planes read with coalesced 128-byte warp requests, everything else in registers.
-#include "common.cuh"
+#include "tail_common.cuh"
 
 namespace mvster {
 
@@ -31,36 +31,24 @@ __global__ void __launch_bounds__(256) tail_kernel(const TailParams p) {
     const float* hy = p.hypo + b * D * p.plane + r;
     float* at = p.attn + b * D * p.plane + r;
 
-    float depth, h1 = 0.f, h2 = 0.f, lmax, lsum = 0.f;
     if constexpr (DT > 0) {
-        float l[DT > 0 ? DT : 1], h[DT > 0 ? DT : 1];
+        float l[DT > 0 ? DT : 1], h[DT > 0 ? DT : 1], a[DT > 0 ? DT : 1];
 #pragma unroll
         for (int d = 0; d < DT; ++d) l[d] = ldg_stream(lg + d * p.plane);
 #pragma unroll
         for (int d = 0; d < DT; ++d) h[d] = ldg_stream(hy + d * p.plane);
-        lmax = l[0];
+        const TailOut r = tail_pixel<(DT > 0 ? DT : 2)>(l, h, p.mode, p.split_itv, a);
 #pragma unroll
-        for (int d = 0; d < DT; ++d) { lmax = fmaxf(lmax, l[d]); lsum += l[d]; }
-        float e[DT > 0 ? DT : 1], es = 0.f;
-#pragma unroll
-        for (int d = 0; d < DT; ++d) { e[d] = expf(l[d] - lmax); es += e[d]; }
-        // arg-max over the softmax values, first maximum wins (torch.max semantics, reference :1129)
-        float best = -1.f, reg = 0.f;
-        int bi = 0;
-#pragma unroll
-        for (int d = 0; d < DT; ++d) {
-            const float a = e[d] / es;
-            stg_stream(at + d * p.plane, a);
-            if (a > best) { best = a; bi = d; }
-            reg = fmaf(a, h[d], reg);
+        for (int d = 0; d < DT; ++d) stg_stream(at + d * p.plane, a[d]);
+        p.depth[i] = r.depth;
+        if (p.conf != nullptr) p.conf[i] = r.conf;
+        if (p.inv_min != nullptr) {
+            p.inv_min[i] = r.inv_min;
+            p.inv_max[i] = r.inv_max;
         }
-        depth = h[0];
-#pragma unroll
-        for (int d = 1; d < DT; ++d) depth = (bi == d) ? h[d] : depth;
-        if (p.mode == MVSTER_DEPTH_REGRESS) depth = reg;
-        h1 = h[1];
-        h2 = h[DT > 2 ? 2 : 1];
+        return;
     } else {
+        float depth, h1 = 0.f, h2 = 0.f, lmax, lsum = 0.f;
         lmax = lg[0];
         for (int d = 0; d < D; ++d) { const float v = lg[d * p.plane]; lmax = fmaxf(lmax, v); lsum += v; }
         float es = 0.f;
@@ -77,16 +65,16 @@ __global__ void __launch_bounds__(256) tail_kernel(const TailParams p) {
             if (d == 2) h2 = h;
         }
         if (p.mode == MVSTER_DEPTH_REGRESS) depth = reg;
-    }
-    p.depth[i] = depth;
-    // photometric confidence on the raw logits: max / sum (reference :1109-1113,1138)
-    if (p.conf != nullptr) p.conf[i] = lmax / lsum;
-    if (p.inv_min != nullptr) {
-        // last_depth_itv = 1/hypo[:,2] - 1/hypo[:,1]  (reference :1152)
-        const float itv = 1.0f / h2 - 1.0f / h1;
-        const float inv = 1.0f / depth;
-        p.inv_min[i] = inv + p.split_itv * itv;
-        p.inv_max[i] = inv - p.split_itv * itv;
+        p.depth[i] = depth;
+        // photometric confidence on the raw logits: max / sum (reference :1109-1113,1138)
+        if (p.conf != nullptr) p.conf[i] = lmax / lsum;
+        if (p.inv_min != nullptr) {
+            // last_depth_itv = 1/hypo[:,2] - 1/hypo[:,1]  (reference :1152)
+            const float itv = 1.0f / h2 - 1.0f / h1;
+            const float inv = 1.0f / depth;
+            p.inv_min[i] = inv + p.split_itv * itv;
+            p.inv_max[i] = inv - p.split_itv * itv;
+        }
     }
 }
 

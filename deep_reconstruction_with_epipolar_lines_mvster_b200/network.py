@@ -1,0 +1,263 @@
+"""Callers of the hot path, widened per SURVEY.md §8f: a checkpoint-compatible ``MVS4net`` whose stage loop runs on the
+fused kernels of this library.
+
+The reference network (models/MVS4Net.py:16-199, models/mvs4net_utils.py:426-509 ``FPN4``, :884-926 ``reg2d``) is
+re-stated here with the *same module / parameter names* so that ``load_state_dict`` of a reference checkpoint works
+unchanged.  What differs is how it executes on a B200:
+
+  * feature extraction runs ONCE on all N views stacked along the batch (the reference loops over views,
+    MVS4Net.py:78-80) and in ``channels_last``, so the NHWC feature maps the fused K1 kernel gathers from are produced
+    directly by the convolutions - no layout conversion at the K1 boundary;
+  * the per-stage hot path (hypothesis schedule, homography composition, warp + correlation + epipolar attention,
+    tail) is the CUDA library behind ``stagenet``;
+  * in eval mode ``reg2d`` hands its last three layers (transposed conv ``conv11`` + BN + ReLU, skip add, ``prob``) to
+    one fused CUDA kernel together with the stagenet tail (``mvster_regtail``), so the full
+    resolution ``[B,8,D,H,W]`` activation and the logits never travel through HBM.
+
+FPN4 and the inner layers of reg2d stay dense cuDNN convolutions (library code, as in the reference).
+Only the shipped configuration family is supported: ``arch_mode='fpn'``, ``reg_net='reg2d'``, no DCN / ASFF / mono
+decoder / positional encoding; anything else raises ``NotImplementedError`` instead of silently diverging.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .stagenet import init_inverse_range, schedule_inverse_range, stagenet
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# building blocks (parameter names follow the reference so that checkpoints load)
+# ----------------------------------------------------------------------------------------------------------------------
+class Conv2d(nn.Module):
+    """conv -> BatchNorm2d -> ReLU (reference mvs4net_utils.py:231-258, the ``gn=False`` branch)."""
+
+    def __init__(self, cin: int, cout: int, kernel_size: int, stride: int = 1, padding: int = 0, relu: bool = True):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size, stride=stride, padding=padding, bias=False)
+        self.bn = nn.BatchNorm2d(cout, momentum=0.1)
+        self.relu = relu
+
+    def forward(self, x):
+        x = self.bn(self.conv(x))
+        return F.relu(x, inplace=True) if self.relu else x
+
+
+class FPN4(nn.Module):
+    """Four-level feature pyramid, 8/4/2/1 x ``base_channels`` output channels at 1/8 .. 1/1 resolution
+    (reference mvs4net_utils.py:426-509, ``gn=False, dcn=False``)."""
+
+    def __init__(self, base_channels: int = 8, gn: bool = False, dcn: bool = False):
+        super().__init__()
+        if gn or dcn:
+            raise NotImplementedError("FPN4(B200): GroupNorm / deformable-conv variants are not built")
+        c = base_channels
+        self.base_channels = c
+        self.conv0 = nn.Sequential(Conv2d(3, c, 3, 1, 1), Conv2d(c, c, 3, 1, 1))
+        self.conv1 = nn.Sequential(Conv2d(c, 2 * c, 5, 2, 2), Conv2d(2 * c, 2 * c, 3, 1, 1), Conv2d(2 * c, 2 * c, 3, 1, 1))
+        self.conv2 = nn.Sequential(Conv2d(2 * c, 4 * c, 5, 2, 2), Conv2d(4 * c, 4 * c, 3, 1, 1), Conv2d(4 * c, 4 * c, 3, 1, 1))
+        self.conv3 = nn.Sequential(Conv2d(4 * c, 8 * c, 5, 2, 2), Conv2d(8 * c, 8 * c, 3, 1, 1), Conv2d(8 * c, 8 * c, 3, 1, 1))
+        top = 8 * c
+        self.inner1 = nn.Conv2d(4 * c, top, 1, bias=True)
+        self.inner2 = nn.Conv2d(2 * c, top, 1, bias=True)
+        self.inner3 = nn.Conv2d(c, top, 1, bias=True)
+        self.out1 = nn.Conv2d(top, 8 * c, 1, bias=False)
+        self.out2 = nn.Conv2d(top, 4 * c, 3, padding=1, bias=False)
+        self.out3 = nn.Conv2d(top, 2 * c, 3, padding=1, bias=False)
+        self.out4 = nn.Conv2d(top, c, 3, padding=1, bias=False)
+        self.out_channels = [8 * c, 4 * c, 2 * c, c]
+
+    @staticmethod
+    def _up(x):
+        return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+
+    def forward(self, x) -> Dict[str, torch.Tensor]:
+        c0 = self.conv0(x)
+        c1 = self.conv1(c0)
+        c2 = self.conv2(c1)
+        top = self.conv3(c2)
+        out = {"stage1": self.out1(top)}
+        top = self._up(top) + self.inner1(c2)
+        out["stage2"] = self.out2(top)
+        top = self._up(top) + self.inner2(c1)
+        out["stage3"] = self.out3(top)
+        top = self._up(top) + self.inner3(c0)
+        out["stage4"] = self.out4(top)
+        return out
+
+
+class ConvBnReLU3D(nn.Module):
+    """reference mvs4net_utils.py:123-130"""
+
+    def __init__(self, cin, cout, kernel_size=3, stride=1, pad=1):
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, kernel_size, stride=stride, padding=pad, bias=False)
+        self.bn = nn.BatchNorm3d(cout)
+
+    def forward(self, x):
+        return F.relu(self.bn(self.conv(x)), inplace=True)
+
+
+def _up3d(cin, cout):
+    return nn.Sequential(
+        nn.ConvTranspose3d(cin, cout, kernel_size=(1, 3, 3), padding=(0, 1, 1), output_padding=(0, 1, 1),
+                           stride=(1, 2, 2), bias=False),
+        nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
+
+
+class reg2d(nn.Module):
+    """Cost regulariser (reference mvs4net_utils.py:884-926): a 3-level U-Net over (H, W) with (1,3,3) strided and
+    (3,3,3) plain convolutions, ``[B, G, D, H, W] -> [B, D, H, W]`` logits.
+
+    ``forward(x)`` is the reference computation.  ``forward_fused_tail(x, hypo, split_itv, ...)`` (eval only) stops
+    before ``conv11`` and lets ``ops.regtail`` do ``conv0 + relu(bn(conv11(.)))`` -> ``prob`` -> softmax / arg-max /
+    confidence / inverse range in one kernel.
+    """
+
+    def __init__(self, input_channel=128, base_channel=32, conv_name="ConvBnReLU3D"):
+        super().__init__()
+        if conv_name != "ConvBnReLU3D":
+            raise NotImplementedError("reg2d(B200): only agg_type='ConvBnReLU3D' is built (attention variants "
+                                      "ConvBnReLU3D_CAM/PAM/... are not used by any shipped config)")
+        c = base_channel
+        k, p = (1, 3, 3), (0, 1, 1)
+        self.conv0 = ConvBnReLU3D(input_channel, c, kernel_size=k, pad=p)
+        self.conv1 = ConvBnReLU3D(c, 2 * c, kernel_size=k, stride=(1, 2, 2), pad=p)
+        self.conv2 = ConvBnReLU3D(2 * c, 2 * c)
+        self.conv3 = ConvBnReLU3D(2 * c, 4 * c, kernel_size=k, stride=(1, 2, 2), pad=p)
+        self.conv4 = ConvBnReLU3D(4 * c, 4 * c)
+        self.conv5 = ConvBnReLU3D(4 * c, 8 * c, kernel_size=k, stride=(1, 2, 2), pad=p)
+        self.conv6 = ConvBnReLU3D(8 * c, 8 * c)
+        self.conv7 = _up3d(8 * c, 4 * c)
+        self.conv9 = _up3d(4 * c, 2 * c)
+        self.conv11 = _up3d(2 * c, c)
+        self.prob = nn.Conv3d(8, 1, 1, stride=1, padding=0)  # the reference hard-codes 8 (mvs4net_utils.py:914)
+        self._folded = None
+
+    def _trunk(self, x):
+        conv0 = self.conv0(x)
+        conv2 = self.conv2(self.conv1(conv0))
+        conv4 = self.conv4(self.conv3(conv2))
+        x = self.conv6(self.conv5(conv4))
+        x = conv4 + self.conv7(x)
+        x = conv2 + self.conv9(x)
+        return conv0, x
+
+    def forward(self, x):
+        conv0, x = self._trunk(x)
+        x = conv0 + self.conv11(x)
+        return self.prob(x).squeeze(1)
+
+    # ---- fused last layers + tail -----------------------------------------------------------------------------------
+    def fused_tail_supported(self) -> bool:
+        return (not self.training) and self.conv11[0].out_channels == 8 and self.conv11[0].in_channels == 16
+
+    def _fold(self):
+        """conv11's BatchNorm (eval) folded into the transposed-conv weight, as HOST tensors: ``w [ky,kx,ci,co]`` and
+        ``params = [bn shift (8), prob weight (8), prob bias]`` (cached until a parameter changes)."""
+        deconv, bn = self.conv11[0], self.conv11[1]
+        key = tuple(t._version for t in (deconv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                         self.prob.weight, self.prob.bias)) + (deconv.weight.data_ptr(),)
+        if self._folded is None or self._folded[0] != key:
+            scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+            shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+            w = deconv.weight.detach().double()[:, :, 0] * scale.view(1, -1, 1, 1)        # [ci, co, ky, kx]
+            w = w.permute(2, 3, 0, 1).contiguous().float().cpu()                          # [ky, kx, ci, co]
+            params = torch.cat([shift.float().cpu(), self.prob.weight.detach().reshape(-1).float().cpu(),
+                                self.prob.bias.detach().reshape(-1).float().cpu()]).contiguous()
+            self._folded = (key, w, params)
+        return self._folded[1], self._folded[2]
+
+    def forward_fused_tail(self, x, depth_hypo, split_itv, inverse_depth=True, depth_mode=ops.DEPTH_ARGMAX):
+        if not self.fused_tail_supported():
+            raise RuntimeError("reg2d.forward_fused_tail: eval mode and base_channel == 8 required")
+        conv0, low = self._trunk(x)
+        w, params = self._fold()
+        return ops.regtail(low, conv0, w, params, depth_hypo, float(split_itv), bool(inverse_depth), depth_mode)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the network
+# ----------------------------------------------------------------------------------------------------------------------
+class MVS4net(nn.Module):
+    """Reference ``MVS4net`` (models/MVS4Net.py:16) on the B200 hot path: same constructor arguments, same
+    ``forward(imgs, proj_matrices, depth_values, filename=None)`` and the same nested output dictionary."""
+
+    def __init__(self, arch_mode="fpn", reg_net="reg2d", num_stage=4, fpn_base_channel=8, reg_channel=8,
+                 stage_splits=(8, 8, 4, 4), depth_interals_ratio=(0.5, 0.5, 0.5, 1), group_cor=False,
+                 group_cor_dim=(8, 8, 8, 8), inverse_depth=False, agg_type="ConvBnReLU3D", dcn=False, pos_enc=0,
+                 mono=False, mono_stg_itrpl="nearest", asff=False, attn_temp=2, attn_fuse_d=True, vis_ETA=False,
+                 vis_stg_features=False, debug=0, *, fuse_regnet_tail: bool = True,
+                 feature_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        unsupported = {"arch_mode": arch_mode != "fpn", "reg_net": reg_net != "reg2d", "dcn": bool(dcn),
+                       "asff": bool(asff), "mono": bool(mono), "vis_ETA": bool(vis_ETA), "debug": bool(debug),
+                       "inverse_depth=False": not inverse_depth}
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError("MVS4net(B200): unsupported option(s) %s - only the shipped fpn / reg2d / "
+                                      "inverse-depth configuration is built (schedule_range is broken upstream, "
+                                      "mvs4net_utils.py:102)" % ", ".join(bad))
+        self.arch_mode, self.num_stage = arch_mode, num_stage
+        self.depth_interals_ratio = list(depth_interals_ratio)
+        self.group_cor, self.group_cor_dim = group_cor, list(group_cor_dim)
+        self.inverse_depth = inverse_depth
+        self.stage_splits = list(stage_splits)
+        self.pos_enc, self.mono, self.asff, self.debug = pos_enc, mono, asff, debug
+        self.attn_ob = nn.ModuleList()
+        self.pos_enc_func = nn.ModuleList()
+        self.feature = FPN4(base_channels=fpn_base_channel)
+        self.stagenet = stagenet(inverse_depth, mono, attn_fuse_d, vis_ETA, attn_temp, debug=debug,
+                                 feature_dtype=feature_dtype)
+        self.reg = nn.ModuleList()
+        for idx in range(num_stage):
+            in_dim = self.group_cor_dim[idx] if group_cor else self.feature.out_channels[idx]
+            self.reg.append(reg2d(input_channel=in_dim, base_channel=reg_channel, conv_name=agg_type))
+        self.fuse_regnet_tail = fuse_regnet_tail
+
+    # ---- step 1: features -------------------------------------------------------------------------------------------
+    def extract_features(self, imgs: Sequence[torch.Tensor]) -> List[Dict[str, torch.Tensor]]:
+        """Per-view stage dictionaries, NHWC in memory.  Eval: one FPN pass over all views (BatchNorm uses running
+        statistics, so stacking views along the batch is the same arithmetic as the reference's per-view loop);
+        training: per view, as the reference, because batch statistics depend on what is in the batch."""
+        n = len(imgs)
+        if self.training:
+            return [self.feature(img.contiguous(memory_format=torch.channels_last)) for img in imgs]
+        b = imgs[0].shape[0]
+        stacked = torch.cat(list(imgs), 0).contiguous(memory_format=torch.channels_last)
+        out = self.feature(stacked)
+        return [{k: v[i * b:(i + 1) * b] for k, v in out.items()} for i in range(n)]
+
+    # ---- forward ------------------------------------------------------------------------------------------------------
+    def forward(self, imgs, proj_matrices, depth_values, filename=None):
+        features = self.extract_features(imgs)
+        outputs = {}
+        stage_out = None
+        for s in range(self.num_stage):
+            key = "stage%d" % (s + 1)
+            feats = [f[key] for f in features]
+            proj = proj_matrices[key]
+            h, w = feats[0].shape[2:]
+            d = self.stage_splits[s]
+            if s == 0:
+                hypo = init_inverse_range(depth_values, d, None, None, h, w)
+            else:
+                hypo = schedule_inverse_range(stage_out["inverse_min_depth"].detach(),
+                                              stage_out["inverse_max_depth"].detach(), d, h, w)
+            regnet = self.reg[s]
+            fused = (self.fuse_regnet_tail and not self.training and not torch.is_grad_enabled()
+                     and regnet.fused_tail_supported() and d in (4, 8))
+            if fused:
+                stage_out = self.stagenet.forward_fused_regnet(feats, proj, hypo, regnet, s, group_cor=self.group_cor,
+                                                               group_cor_dim=self.group_cor_dim[s],
+                                                               split_itv=self.depth_interals_ratio[s])
+            else:
+                stage_out = self.stagenet(feats, proj, depth_hypo=hypo, regnet=regnet, stage_idx=s,
+                                          group_cor=self.group_cor, group_cor_dim=self.group_cor_dim[s],
+                                          split_itv=self.depth_interals_ratio[s], fn=filename)
+            outputs[key] = stage_out
+        return outputs

@@ -217,6 +217,40 @@ def tail(logits: torch.Tensor, hypo: torch.Tensor, split_itv: float, want_conf: 
     return attn, depth, conf, inv_min, inv_max
 
 
+def regtail(low: torch.Tensor, skip: torch.Tensor, w_host: torch.Tensor, params_host: torch.Tensor,
+            hypo: torch.Tensor, split_itv: float, inverse_depth: bool, depth_mode: int = DEPTH_ARGMAX,
+            want_conf: bool = True):
+    """K2a': ``skip + relu(bn(conv11(low)))`` -> ``prob`` -> tail in one kernel (reference mvs4net_utils.py:923-926 +
+    :1109-1156, eval mode).  ``low`` [B,16,D,H/2,W/2] and ``skip`` [B,8,D,H,W] are CUDA fp32 NCDHW; ``w_host``
+    [3,3,16,8] (BatchNorm-folded transposed-conv weight, ``[ky][kx][ci][co]``) and ``params_host`` [17] (BN shift,
+    prob weight, prob bias) are CPU fp32 tensors - they are passed to the kernel by value.
+    Returns ``(attn, depth, conf, inv_min, inv_max)`` like :func:`tail`."""
+    _require_cuda(low, "low")
+    low, skip, hy = _f32c(low, "low"), _f32c(skip, "skip"), _f32c(hypo, "depth_hypo")
+    if low.dim() != 5 or skip.dim() != 5 or low.shape[1] != 16 or skip.shape[1] != 8:
+        raise RuntimeError("regtail: low must be [B,16,D,H/2,W/2] and skip [B,8,D,H,W], got %s / %s"
+                           % (tuple(low.shape), tuple(skip.shape)))
+    b, _, d, h, w = skip.shape
+    if tuple(low.shape) != (b, 16, d, h // 2, w // 2) or tuple(hy.shape) != (b, d, h, w) or h % 2 or w % 2:
+        raise RuntimeError("regtail: inconsistent shapes low %s skip %s hypo %s"
+                           % (tuple(low.shape), tuple(skip.shape), tuple(hy.shape)))
+    if w_host.device.type != "cpu" or params_host.device.type != "cpu" or w_host.dtype != torch.float32 \
+            or params_host.dtype != torch.float32 or w_host.numel() != 1152 or params_host.numel() != 17 \
+            or not w_host.is_contiguous() or not params_host.is_contiguous():
+        raise RuntimeError("regtail: w_host [3,3,16,8] and params_host [17] must be contiguous CPU fp32 tensors")
+    dev = skip.device
+    attn = torch.empty((b, d, h, w), device=dev, dtype=torch.float32)
+    depth = torch.empty((b, h, w), device=dev, dtype=torch.float32)
+    conf = torch.empty((b, h, w), device=dev, dtype=torch.float32) if want_conf else None
+    inv_min = torch.empty((b, h, w), device=dev, dtype=torch.float32) if inverse_depth else None
+    inv_max = torch.empty((b, h, w), device=dev, dtype=torch.float32) if inverse_depth else None
+    _lib.check(_lib.load().mvster_regtail(
+        _ptr(low), _ptr(skip), ctypes.c_void_p(w_host.data_ptr()), ctypes.c_void_p(params_host.data_ptr()), _ptr(hy),
+        float(split_itv), int(depth_mode), _ptr(attn), _ptr(depth), _ptr(conf), _ptr(inv_min), _ptr(inv_max),
+        b, d, h, w, _stream(skip)))
+    return attn, depth, conf, inv_min, inv_max
+
+
 def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:
     b, d, h, w = attn.shape
     g_attn = None if g_attn is None else _f32c(g_attn, "grad attn")

@@ -94,6 +94,31 @@ class stagenet(nn.Module):
             ret_dict["mono_feat"] = ref_feature
         return ret_dict
 
+    def forward_fused_regnet(self, features, proj_matrices, depth_hypo, regnet, stage_idx, group_cor=False,
+                             group_cor_dim=8, split_itv=1):
+        """Inference-only variant of ``forward`` for a ``network.reg2d`` regulariser: the last layers of ``regnet``
+        (transposed conv + BN + ReLU, skip add, ``prob``) and steps 3-4 run as ONE kernel (``ops.regtail``), so the
+        logits are never materialised.  Same return dictionary as ``forward``."""
+        if self.training or torch.is_grad_enabled():
+            raise RuntimeError("stagenet.forward_fused_regnet is inference-only (eval mode under torch.no_grad())")
+        ref_feature = features[0]
+        if group_cor and self.attn_fuse_d:
+            cor_feats = EpipolarAggregate.apply(ref_feature, depth_hypo, proj_matrices, int(group_cor_dim),
+                                                float(self.attn_temp), self.feature_dtype, *features[1:])
+        else:
+            cor_feats = epipolar_aggregate_variant(features, proj_matrices, depth_hypo, bool(group_cor), int(group_cor_dim),
+                                                   bool(self.attn_fuse_d), float(self.attn_temp))
+        attn_weight, depth, conf, inv_min, inv_max = regnet.forward_fused_tail(
+            cor_feats, depth_hypo, float(split_itv), bool(self.inverse_depth), self.depth_mode)
+        ret_dict = {"depth": depth, "photometric_confidence": conf, "hypo_depth": depth_hypo,
+                    "attn_weight": attn_weight}
+        if self.inverse_depth:
+            ret_dict["inverse_min_depth"] = inv_min
+            ret_dict["inverse_max_depth"] = inv_max
+        if self.mono:
+            ret_dict["mono_feat"] = ref_feature
+        return ret_dict
+
 
 FusedStageNet = stagenet
 

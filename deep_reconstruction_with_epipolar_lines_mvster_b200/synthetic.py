@@ -152,3 +152,38 @@ def pair_list(nviews: int, nsrc: int) -> np.ndarray:
         others = sorted((v for v in range(nviews) if v != r), key=lambda v: (abs(v - r), v))
         pairs[r] = others[:nsrc]
     return pairs
+
+
+def fill_state_dict(state_dict, seed: int = 0):
+    """Deterministic, framework-independent synthetic weights for a (reference or B200) ``MVS4net``: every entry is
+    drawn from a NumPy stream seeded by ``crc32(key) + seed``, so the same recipe applied to two models with the same
+    parameter names gives identical weights - no checkpoint has to be stored with the golden fixtures.
+    Conv weights ~ N(0, 2/fan_in) (N(0, 0.5/fan_in) for the layers without ReLU); BatchNorm weight ~ U(0.8,1.2), bias / running_mean ~ N(0,0.1),
+    running_var ~ U(0.5,1.5); conv biases ~ N(0,0.05)."""
+    import zlib
+
+    import torch
+    out = {}
+    for key, val in state_dict.items():
+        rng = np.random.RandomState((zlib.crc32(key.encode()) + seed) % (2 ** 31))
+        shape = tuple(val.shape)
+        if key.endswith("num_batches_tracked"):
+            arr = np.zeros(shape, dtype=np.int64)
+        elif key.endswith("running_var"):
+            arr = rng.uniform(0.5, 1.5, size=shape)
+        elif key.endswith("running_mean"):
+            arr = rng.normal(0.0, 0.1, size=shape)
+        elif key.endswith("weight") and len(shape) == 1:
+            arr = rng.uniform(0.8, 1.2, size=shape)
+        elif key.endswith("weight"):
+            fan_in = int(np.prod(shape[1:]))
+            # layers without a ReLU behind them (FPN lateral / output convs, prob) get gain 1/2 so that features and
+            # logits stay O(1) through the whole network
+            linear = any(t in key for t in (".inner", ".out", ".prob."))
+            arr = rng.normal(0.0, np.sqrt((0.5 if linear else 2.0) / fan_in), size=shape)
+        elif ".bn." in key or key.split(".")[-2].isdigit():
+            arr = rng.normal(0.0, 0.1, size=shape)
+        else:
+            arr = rng.normal(0.0, 0.05, size=shape)
+        out[key] = torch.from_numpy(np.asarray(arr)).to(val.dtype)
+    return out

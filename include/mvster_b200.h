@@ -126,6 +126,21 @@ int mvster_schedule_inverse_range(const float* inv_min, const float* inv_max, fl
  */
 int mvster_tail(const float* logits, const float* hypo, float split_itv, int depth_mode, float* attn, float* depth,
                 float* conf, float* inv_min, float* inv_max, int B, int D, int H, int W, void* stream);
+/* ---- K2a': last layers of the cost regulariser fused with the tail ---------------
+ * Replaces, in eval mode, reg2d.forward's `x = conv0 + self.conv11(x); x = self.prob(x)` (models/mvs4net_utils.py:
+ * 923-926; conv11 = ConvTranspose3d(16,8,(1,3,3),stride (1,2,2)) + BatchNorm3d + ReLU, prob = Conv3d(8,1,1)) AND the
+ * stagenet tail (:1109-1156) with one kernel: the full-resolution [B,8,D,H,W] activation and the logits never
+ * reach HBM.
+ *   low     dev  [B, 16, D, H/2, W/2] input of conv11 (NCDHW, fp32)
+ *   skip    dev  [B,  8, D, H,   W  ] conv0 output (NCDHW, fp32)
+ *   w       HOST [3, 3, 16, 8]  conv11 weight as [ky][kx][ci][co] with the BatchNorm scale folded in
+ *   params  HOST [17]           BatchNorm shift[8] (beta - mean*scale), prob weight[8], prob bias
+ *   the remaining arguments are those of mvster_tail.  D in {4, 8}; H, W even.
+ * The weights are host pointers because they travel as kernel parameters (constant bank), read by FFMA directly.
+ */
+int mvster_regtail(const float* low, const float* skip, const float* w, const float* params, const float* hypo,
+                   float split_itv, int depth_mode, float* attn, float* depth, float* conf, float* inv_min,
+                   float* inv_max, int B, int D, int H, int W, void* stream);
 /* backward of the tail w.r.t. the logits: softmax backward of g_attn (+ the regression term of g_depth when
  * depth_mode == MVSTER_DEPTH_REGRESS); g_attn / g_depth may be NULL (treated as zero) */
 int mvster_tail_bwd(const float* attn, const float* hypo, const float* depth, const float* g_attn,

@@ -331,6 +331,36 @@ def tail_np(logits: np.ndarray, hypo: np.ndarray, split_itv: float, training: bo
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# K2a': last layers of reg2d (eval) + tail                                  models/mvs4net_utils.py:899-926,1109-1156
+# ---------------------------------------------------------------------------------------------------------------
+def reg2d_last_layers_np(low: np.ndarray, skip: np.ndarray, deconv_w: np.ndarray, bn_weight: np.ndarray,
+                         bn_bias: np.ndarray, bn_mean: np.ndarray, bn_var: np.ndarray, prob_w: np.ndarray,
+                         prob_b: float, eps: float = 1e-5) -> np.ndarray:
+    """float64 restatement of ``x = conv0 + relu(bn(conv11(x))); logits = prob(x)`` (:923-926) in eval mode.
+
+    ``low`` [B,Ci,D,h,w]; ``skip`` [B,Co,D,2h,2w]; ``deconv_w`` [Ci,Co,1,3,3] (ConvTranspose3d weight layout,
+    stride (1,2,2), padding (0,1,1), output_padding (0,1,1): out[y] gathers in[iy] with y = 2*iy - 1 + ky).
+    Returns the logits [B,D,2h,2w] as float64."""
+    low = low.astype(np.float64)
+    b, ci, d, h, w = low.shape
+    co = deconv_w.shape[1]
+    wt = deconv_w.astype(np.float64)[:, :, 0]
+    out = np.zeros((b, co, d, 2 * h, 2 * w), dtype=np.float64)
+    for ky in range(3):
+        for kx in range(3):
+            contrib = np.einsum("bcdyx,ck->bkdyx", low, wt[:, :, ky, kx])
+            ys = 2 * np.arange(h) - 1 + ky
+            xs = 2 * np.arange(w) - 1 + kx
+            vy, vx = (ys >= 0) & (ys < 2 * h), (xs >= 0) & (xs < 2 * w)
+            out[:, :, :, ys[vy][:, None], xs[vx][None, :]] += contrib[:, :, :, vy][:, :, :, :, vx]
+    scale = bn_weight.astype(np.float64) / np.sqrt(bn_var.astype(np.float64) + eps)
+    shift = bn_bias.astype(np.float64) - bn_mean.astype(np.float64) * scale
+    out = out * scale[None, :, None, None, None] + shift[None, :, None, None, None]
+    x = skip.astype(np.float64) + np.maximum(out, 0.0)
+    return np.einsum("bcdyx,c->bdyx", x, prob_w.astype(np.float64).reshape(-1)) + float(prob_b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # K2b: geometric consistency filter + mask fusion                                     test_mvs4.py:612-670,716-749
 # ---------------------------------------------------------------------------------------------------------------
 def remap_linear_np(img: np.ndarray, mapx: np.ndarray, mapy: np.ndarray) -> np.ndarray:

@@ -8,6 +8,7 @@
   train    config 4 (single GPU part): K1 forward+backward at 512x640, B=2, N=5 through EpipolarAggregate
   filter   config 5: 49 views 512x640, 9 sources each, fused geometric/photometric filter
   ref_gpu  plain-PyTorch (eager, stock ATen kernels) restatement of the same op on the same GPU, as context
+  network  whole MVS4net.forward (FPN4 + reg2d via cuDNN, fused stagenet / regulariser tail) vs the eager op sequence
 """
 from __future__ import annotations
 
@@ -198,15 +199,92 @@ def bench_ref_gpu_train(args, dev):
                           "eager_peak_MB": e_mem / 1e6, "fused_peak_MB": f_mem / 1e6}))
 
 
+NET_CFG = dict(arch_mode="fpn", reg_net="reg2d", num_stage=4, fpn_base_channel=8, reg_channel=8,
+               stage_splits=[8, 8, 4, 4], depth_interals_ratio=[0.5, 0.5, 0.5, 1.0], group_cor=True,
+               group_cor_dim=[8, 8, 4, 4], inverse_depth=True, agg_type="ConvBnReLU3D", attn_temp=2.0, attn_fuse_d=True)
+
+
+class _EagerStagenet(torch.nn.Module):
+    """The reference's stagenet op sequence in eager PyTorch (stock ATen kernels) - SURVEY §8d row (iii) on the GPU
+    box, where /root/reference itself is not available: the oracle's op-for-op port + the torch tail."""
+
+    def forward(self, features, proj_matrices, depth_hypo, regnet, stage_idx, group_cor=True, group_cor_dim=8,
+                split_itv=1, fn=None):
+        from oracle import mvster_oracle as O
+        vol = O.epipolar_aggregate_port([f.contiguous() for f in features], proj_matrices, depth_hypo, group_cor_dim, 2.0)
+        logits = regnet(vol)
+        conf = logits.max(1)[0] / logits.sum(1)
+        attn = torch.softmax(logits, 1)
+        idx = attn.argmax(1, keepdim=True)
+        depth = torch.gather(depth_hypo, 1, idx).squeeze(1)
+        itv = 1.0 / depth_hypo[:, 2] - 1.0 / depth_hypo[:, 1]
+        return {"depth": depth, "photometric_confidence": conf, "hypo_depth": depth_hypo, "attn_weight": attn,
+                "inverse_min_depth": 1.0 / depth + split_itv * itv, "inverse_max_depth": 1.0 / depth - split_itv * itv}
+
+
+def bench_network(args, dev):
+    """whole MVS4net.forward, images in -> 4-stage depth out, DTU as-loaded shape
+    832x1152 (reg2d needs multiples of 64), N=5, one scene per call."""
+    h0, w0, n, b = 832, 1152, 5, 1
+    model = mv.MVS4net(**NET_CFG).eval()
+    model.load_state_dict(syn.fill_state_dict(model.state_dict(), seed=7))
+    model = model.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    imgs = [torch.rand((b, 3, h0, w0), device=dev, generator=gen) for _ in range(n)]
+    proj = {k: torch.from_numpy(v).to(dev) for k, v in syn.proj_matrices_all_stages(b, n, h0, w0).items()}
+    dv = torch.from_numpy(syn.depth_values(b)).to(dev)
+    fused_stagenet = model.stagenet
+    res = {}
+    its = max(3, args.iters // 4)
+
+    def run():
+        with torch.no_grad():
+            return model(imgs, proj, dv)
+
+    for name, tf32, fuse, eager in (("b200_fused_fp32", False, True, False), ("b200_unfused_fp32", False, False, False),
+                                    ("b200_fused_tf32", True, True, False), ("eager_reference_like_fp32", False, False, True),
+                                    ("eager_reference_like_tf32", True, False, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        model.fuse_regnet_tail = fuse
+        model.stagenet = _EagerStagenet() if eager else fused_stagenet
+        if eager:   # the reference extracts features view by view in NCHW
+            model.extract_features = lambda ims: [model.feature(i) for i in ims]
+        elif "extract_features" in model.__dict__:
+            del model.__dict__["extract_features"]
+        torch.cuda.reset_peak_memory_stats()
+        res[name + "_ms"] = timed(run, its)
+        res[name + "_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
+    # where the time goes on the B200 path (fused, fp32)
+    torch.backends.cudnn.allow_tf32 = False
+    model.stagenet, model.fuse_regnet_tail = fused_stagenet, True
+    with torch.no_grad():
+        res["fpn_ms"] = timed(lambda: model.extract_features(imgs), its)
+        vol = torch.randn((b, 4, 4, h0, w0), device=dev)
+        hyp = torch.rand((b, 4, h0, w0), device=dev) * 400 + 450
+        res["reg2d_stage4_unfused_plus_tail_ms"] = timed(lambda: ops.tail(model.reg[3](vol), hyp, 1.0, True, True), its)
+        res["reg2d_stage4_fused_tail_ms"] = timed(lambda: model.reg[3].forward_fused_tail(vol, hyp, 1.0), its)
+        conv0, low = model.reg[3]._trunk(vol)
+        w, params = model.reg[3]._fold()
+        ms = timed(lambda: ops.regtail(low, conv0, w, params, hyp, 1.0, True), args.iters)
+        res["regtail_kernel_ms"] = ms
+        res["regtail_GFMA_per_s"] = b * 4 * (h0 // 2) * (w0 // 2) * 1152 / ms / 1e6
+        res["regtail_algorithmic_GBps"] = b * 4 * h0 * w0 * (16 / 4 + 8 + 1 + 1 + 1) * 4 / ms / 1e6
+    res.update({"bench": "mvs4net_forward_832x1152_n5", "depth_maps_per_s_b200_fused_fp32": 1e3 * b / res["b200_fused_fp32_ms"],
+                "depth_maps_per_s_eager_fp32": 1e3 * b / res["eager_reference_like_fp32_ms"],
+                "speedup_vs_eager_fp32": res["eager_reference_like_fp32_ms"] / res["b200_fused_fp32_ms"]})
+    print(json.dumps(res))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train")
+    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--cpu-filter-pairs", type=int, default=20)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     fns = {"stages": bench_stages, "binpick": bench_binpick, "train": bench_train, "filter": bench_filter,
-           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train}
+           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network}
     for name in args.which.split(","):
         fns[name](args, dev)
 

@@ -1,0 +1,156 @@
+"""GPU parity of the widened scope: the fused regulariser-tail kernel (``mvster_regtail``) against its
+float64 oracle and against the reference's golden vectors, and the whole ``MVS4net`` forward on the B200 path against
+the unmodified reference's CPU outputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import deep_reconstruction_with_epipolar_lines_mvster_b200 as mv
+from deep_reconstruction_with_epipolar_lines_mvster_b200 import ops, synthetic as syn
+from oracle import mvster_oracle as O
+
+from test_network_host import CFG
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # parity runs compare against the reference's fp32 CPU arithmetic
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.fixture(scope="module")
+def model():
+    m = mv.MVS4net(**CFG).eval()
+    m.load_state_dict(syn.fill_state_dict(m.state_dict(), seed=7))
+    return m.to(DEV)
+
+
+def _decided(attn, eps=1e-5):
+    srt = np.sort(attn, 1)
+    return (srt[:, -1] - srt[:, -2]) > eps
+
+
+@pytest.mark.parametrize("b,d,hh,wh", [(1, 4, 5, 7), (2, 8, 4, 33), (1, 4, 9, 40), (1, 8, 1, 1)])
+def test_regtail_matches_oracle(b, d, hh, wh):
+    rng = np.random.RandomState(100 + d + hh)
+    low = rng.normal(0, 1, (b, 16, d, hh, wh)).astype(np.float32)
+    skip = np.maximum(rng.normal(0, 1, (b, 8, d, 2 * hh, 2 * wh)), 0).astype(np.float32)
+    dw = rng.normal(0, 0.2, (16, 8, 1, 3, 3)).astype(np.float32)
+    bw, bb = rng.uniform(0.8, 1.2, 8).astype(np.float32), rng.normal(0, 0.1, 8).astype(np.float32)
+    bm, bv = rng.normal(0, 0.1, 8).astype(np.float32), rng.uniform(0.5, 1.5, 8).astype(np.float32)
+    pw, pb = rng.normal(0, 0.3, 8).astype(np.float32), 0.05
+    hypo = np.sort(rng.uniform(450, 900, (b, d, 2 * hh, 2 * wh)).astype(np.float32), 1)[:, ::-1].copy()
+    logits = O.reg2d_last_layers_np(low, skip, dw, bw, bb, bm, bv, pw, pb)
+    want = O.tail_np(logits, hypo.astype(np.float64), 0.5)
+    scale = bw.astype(np.float64) / np.sqrt(bv.astype(np.float64) + 1e-5)
+    w = (dw[:, :, 0].astype(np.float64) * scale[None, :, None, None]).transpose(2, 3, 0, 1)
+    params = np.concatenate([bb - bm * scale, pw, [pb]]).astype(np.float32)
+    attn, depth, conf, inv_min, inv_max = ops.regtail(
+        torch.from_numpy(low).to(DEV), torch.from_numpy(skip).to(DEV),
+        torch.from_numpy(np.ascontiguousarray(w).astype(np.float32)), torch.from_numpy(params),
+        torch.from_numpy(hypo).to(DEV), 0.5, True)
+    assert np.abs(attn.cpu().numpy() - want["attn_weight"]).max() < 2e-5
+    ok = _decided(want["attn_weight"])
+    assert (depth.cpu().numpy() == want["depth"].astype(np.float32))[ok].all()
+    assert np.allclose(conf.cpu().numpy(), want["photometric_confidence"], rtol=2e-3, atol=1e-4) or \
+        np.median(np.abs(conf.cpu().numpy() - want["photometric_confidence"])) < 1e-4
+    assert np.allclose(inv_min.cpu().numpy()[ok], want["inverse_min_depth"][ok], rtol=1e-5)
+    assert np.allclose(inv_max.cpu().numpy()[ok], want["inverse_max_depth"][ok], rtol=1e-5)
+
+
+def test_regtail_matches_reference_golden(golden, model):
+    g = golden("network")
+    reg = model.reg[3]
+    w, params = reg._fold()
+    attn, depth, conf, inv_min, inv_max = ops.regtail(
+        torch.from_numpy(g["s4_low"]).to(DEV), torch.from_numpy(g["s4_skip"]).to(DEV), w, params,
+        torch.from_numpy(g["stage4_hypo_depth"]).to(DEV), 1.0, True)
+    assert np.abs(attn.cpu().numpy() - g["stage4_attn_weight"]).max() < 1e-4
+    ok = _decided(g["stage4_attn_weight"], 1e-4)
+    assert (depth.cpu().numpy() == g["stage4_depth"])[ok].all() and ok.mean() > 0.95
+    cref = g["stage4_photometric_confidence"]
+    fin = np.isfinite(cref) & (np.abs(cref) < 50)
+    assert np.allclose(conf.cpu().numpy()[fin], cref[fin], rtol=1e-3, atol=1e-3)
+    assert np.allclose(inv_min.cpu().numpy()[ok], g["stage4_inverse_min_depth"][ok], rtol=1e-6)
+
+
+def test_regtail_equals_unfused_layers_at_stage_size(model):
+    """Fused kernel vs the same module's cuDNN conv11 + BN + ReLU + add + prob followed by the streaming tail kernel,
+    on a 256x320 stage-4-shaped volume: identical arg-max wherever the attention is decided, attention within 1e-5."""
+    reg = model.reg[3]
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn((2, 4, 4, 256, 320), device=DEV, generator=gen)
+    hypo = torch.sort(torch.rand((2, 4, 256, 320), device=DEV, generator=gen) * 400 + 450, 1, descending=True)[0]
+    with torch.no_grad():
+        logits = reg(x)
+        a0, d0, c0, mn0, mx0 = ops.tail(logits, hypo, 1.0, True, True)
+        a1, d1, c1, mn1, mx1 = reg.forward_fused_tail(x, hypo, 1.0)
+    assert (a0 - a1).abs().max().item() < 2e-5
+    ok = torch.from_numpy(_decided(a0.cpu().numpy())).to(DEV)
+    assert torch.equal(d0[ok], d1[ok]) and ok.float().mean().item() > 0.99
+    assert torch.allclose(mn0[ok], mn1[ok], rtol=1e-6)
+
+
+def test_regtail_rejects_bad_arguments(model):
+    w, params = model.reg[3]._fold()
+    low = torch.zeros((1, 16, 4, 4, 4), device=DEV)
+    skip = torch.zeros((1, 8, 4, 8, 8), device=DEV)
+    hypo = torch.ones((1, 4, 8, 8), device=DEV)
+    with pytest.raises(RuntimeError, match="CPU fp32"):
+        ops.regtail(low, skip, w.to(DEV), params, hypo, 1.0, True)
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        ops.regtail(low, skip[..., :6], w, params, hypo, 1.0, True)
+    with pytest.raises(RuntimeError, match="not in"):
+        ops.regtail(torch.zeros((1, 16, 3, 4, 4), device=DEV), torch.zeros((1, 8, 3, 8, 8), device=DEV), w, params,
+                    torch.ones((1, 3, 8, 8), device=DEV), 1.0, True)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_mvs4net_forward_matches_reference(golden, model, fused):
+    """Images in, depth out: the whole network on the B200 path against the unmodified reference on CPU.  Stage 1 is
+    compared directly; later stages are free-running (each consumes the previous stage's arg-max), so they are compared
+    on the pixels whose hypotheses still agree."""
+    g = golden("network")
+    imgs = [torch.from_numpy(g["imgs"][v]).to(DEV) for v in range(g["imgs"].shape[0])]
+    proj = {k: torch.from_numpy(v).to(DEV) for k, v in syn.proj_matrices_all_stages(1, len(imgs), 64, 128).items()}
+    model.fuse_regnet_tail = fused
+    with torch.no_grad():
+        out = model(imgs, proj, torch.from_numpy(g["depth_values"]).to(DEV))
+    for s in range(1, 5):
+        st = "stage%d" % s
+        hyp = out[st]["hypo_depth"].cpu().numpy()
+        same_hyp = np.abs(hyp - g[st + "_hypo_depth"]).max(1) < 1e-3 * np.abs(g[st + "_hypo_depth"]).max(1)
+        assert same_hyp.mean() > (0.999 if s == 1 else 0.9), (st, same_hyp.mean())
+        attn = out[st]["attn_weight"].cpu().numpy()
+        m = np.broadcast_to(same_hyp[:, None], attn.shape)
+        assert np.abs(attn - g[st + "_attn_weight"])[m].max() < 2e-3, st
+        ok = same_hyp & _decided(g[st + "_attn_weight"], 1e-2)
+        # depth within 1e-3 of the depth interval (north-star tolerance); the hypotheses themselves differ by an ulp
+        itv = np.abs(g[st + "_hypo_depth"][:, 1] - g[st + "_hypo_depth"][:, 0])
+        close = np.abs(out[st]["depth"].cpu().numpy() - g[st + "_depth"]) <= 1e-3 * itv
+        assert close[ok].mean() > 0.999, (st, close[ok].mean())
+        assert set(out[st].keys()) == {"depth", "photometric_confidence", "hypo_depth", "attn_weight",
+                                       "inverse_min_depth", "inverse_max_depth"}
+
+
+def test_mvs4net_fused_and_unfused_paths_agree(model):
+    h0, w0, n = 128, 192, 4
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    imgs = [torch.rand((2, 3, h0, w0), device=DEV, generator=gen) for _ in range(n)]
+    proj = {k: torch.from_numpy(v).to(DEV) for k, v in syn.proj_matrices_all_stages(2, n, h0, w0).items()}
+    dv = torch.from_numpy(syn.depth_values(2)).to(DEV)
+    outs = []
+    for fused in (False, True):
+        model.fuse_regnet_tail = fused
+        with torch.no_grad():
+            outs.append(model(imgs, proj, dv))
+    a, b = outs[0]["stage1"], outs[1]["stage1"]
+    assert (a["attn_weight"] - b["attn_weight"]).abs().max().item() < 1e-4
+    same = (outs[0]["stage4"]["depth"] == outs[1]["stage4"]["depth"]).float().mean().item()
+    assert same > 0.98, same
