@@ -1,0 +1,273 @@
+// Direct fp32 convolutions for the high-resolution, few-channel layers of the cost regulariser reg2d
+// (models/mvs4net_utils.py:889-912, eval mode, BatchNorm folded into the weights, ReLU fused) - SURVEY.md §8f rank 1.
+//
+// cuDNN's fp32 kernels are built for wide layers; at 4..32 channels and millions of pixels they run at a few percent
+// of the machine (measured on B200: conv0 + BatchNorm + ReLU of stage 4 take ~5 ms per scene for 1.1 GFMA).  These
+// layers have so few weights (288 .. 6912 floats) that the whole filter bank fits in the kernel-parameter constant
+// bank: a thread keeps a small tile of output pixels x ALL output channels in registers, walks the input channels,
+// and every FFMA takes its weight from a uniform register filled by a uniform constant load (no per-thread weight
+// loads, no shared memory).  Activations are NCDHW fp32 as the reference's; x is the fastest axis, so a warp reads
+// and writes whole 128/256-byte row segments per channel plane.
+//
+//   mode 0  Conv3d(k = (KD,3,3), stride 1, padding (KD/2,1,1))            thread tile 2x2 output pixels
+//   mode 1  Conv3d(k = (1,3,3), stride (1,2,2), padding (0,1,1))          thread tile 1x2 output pixels
+//   mode 2  ConvTranspose3d(k = (1,3,3), stride (1,2,2), padding (0,1,1), output_padding (0,1,1)), optional skip
+//           added AFTER the ReLU (reg2d: x = conv2 + conv9(x))            thread tile 2x2 outputs of one input pixel
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mvster {
+
+constexpr int kScUnroll = 2;  // input channels per loop body (bounded registers; weights come through LDCU)
+
+template <int KD, int CIN, int COUT>
+struct SmallConvParams {
+    float w[KD * 9 * CIN * COUT];  // [kd][ky][kx][ci][co]
+    float bias[COUT];
+    const float* x;
+    const float* skip;
+    float* y;
+    int B, D, H, W;  // INPUT height / width
+    int relu;
+};
+
+__device__ __forceinline__ float ldz(const float* p, bool ok) { return ok ? __ldg(p) : 0.0f; }
+__device__ __forceinline__ float2 ldz2(const float* p, bool ok) {
+    return ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ float4 ldz4(const float* p, bool ok) {
+    return ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- mode 0: stride 1 ------------------------------------------------------------------------------------------
+template <int KD, int CIN, int COUT>
+__global__ void __launch_bounds__(128, 3) smallconv_s1_kernel(const __grid_constant__ SmallConvParams<KD, CIN, COUT> p) {
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int b = blockIdx.z / p.D, d = blockIdx.z % p.D;
+    const int H = p.H, W = p.W;
+    if (2 * i >= W || 2 * j >= H) return;
+    const int x0 = 2 * i, y0 = 2 * j;
+    const size_t plane = (size_t)H * W;
+    float acc[2][2][COUT];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[a][c][co] = 0.0f;
+    const bool vl = x0 > 0, vr = x0 + 2 < W;
+    bool vy[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vy[r] = (unsigned)(y0 - 1 + r) < (unsigned)H;
+#pragma unroll 1
+    for (int kd = 0; kd < KD; ++kd) {
+        const int dz = d + kd - KD / 2;
+        if ((unsigned)dz >= (unsigned)p.D) continue;
+        const float* xp = p.x + (((size_t)b * CIN) * p.D + dz) * plane + (size_t)(y0 - 1) * W + x0;
+        const float* wk = p.w + (size_t)kd * 9 * CIN * COUT;
+#pragma unroll kScUnroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* q = xp + (size_t)ci * p.D * plane;
+            float in[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float* qr = q + (size_t)r * W;
+                const float2 m = ldz2(qr, vy[r]);
+                in[r][0] = ldz(qr - 1, vy[r] && vl);
+                in[r][1] = m.x;
+                in[r][2] = m.y;
+                in[r][3] = ldz(qr + 2, vy[r] && vr);
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) {
+                        const float wv = wk[((ky * 3 + kx) * CIN + ci) * COUT + co];
+                        acc[0][0][co] = fmaf(wv, in[ky][kx], acc[0][0][co]);
+                        acc[0][1][co] = fmaf(wv, in[ky][kx + 1], acc[0][1][co]);
+                        acc[1][0][co] = fmaf(wv, in[ky + 1][kx], acc[1][0][co]);
+                        acc[1][1][co] = fmaf(wv, in[ky + 1][kx + 1], acc[1][1][co]);
+                    }
+        }
+    }
+    float* yp = p.y + (((size_t)b * COUT) * p.D + d) * plane + (size_t)y0 * W + x0;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        float v[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                v[a][c] = acc[a][c][co] + p.bias[co];
+                if (p.relu) v[a][c] = fmaxf(v[a][c], 0.0f);
+            }
+        float* yc = yp + (size_t)co * p.D * plane;
+        *reinterpret_cast<float2*>(yc) = make_float2(v[0][0], v[0][1]);
+        *reinterpret_cast<float2*>(yc + W) = make_float2(v[1][0], v[1][1]);
+    }
+}
+
+// ---- mode 1: stride 2 (KD = 1) ---------------------------------------------------------------------------------
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128, 3) smallconv_s2_kernel(const __grid_constant__ SmallConvParams<1, CIN, COUT> p) {
+    const int Ho = p.H / 2, Wo = p.W / 2;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int b = blockIdx.z / p.D, d = blockIdx.z % p.D;
+    if (2 * i >= Wo || oy >= Ho) return;
+    const int H = p.H, W = p.W;
+    const int xi = 4 * i;  // first input column of the aligned float4; outputs 2i, 2i+1 read columns xi-1 .. xi+3
+    const size_t plane = (size_t)H * W, oplane = (size_t)Ho * Wo;
+    float acc[2][COUT];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[c][co] = 0.0f;
+    bool vy[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) vy[r] = (unsigned)(2 * oy - 1 + r) < (unsigned)H;
+    const bool vl = xi > 0;
+    const float* xp = p.x + (((size_t)b * CIN) * p.D + d) * plane + (size_t)(2 * oy - 1) * W + xi;
+#pragma unroll kScUnroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* q = xp + (size_t)ci * p.D * plane;
+        float in[3][5];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float* qr = q + (size_t)r * W;
+            const float4 m = ldz4(qr, vy[r]);
+            in[r][0] = ldz(qr - 1, vy[r] && vl);
+            in[r][1] = m.x; in[r][2] = m.y; in[r][3] = m.z; in[r][4] = m.w;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float wv = p.w[((ky * 3 + kx) * CIN + ci) * COUT + co];
+                    acc[0][co] = fmaf(wv, in[ky][kx], acc[0][co]);
+                    acc[1][co] = fmaf(wv, in[ky][kx + 2], acc[1][co]);
+                }
+    }
+    float* yp = p.y + (((size_t)b * COUT) * p.D + d) * oplane + (size_t)oy * Wo + 2 * i;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        float v0 = acc[0][co] + p.bias[co], v1 = acc[1][co] + p.bias[co];
+        if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+        *reinterpret_cast<float2*>(yp + (size_t)co * p.D * oplane) = make_float2(v0, v1);
+    }
+}
+
+// ---- mode 2: transposed stride 2 (KD = 1), skip added after the ReLU ----------------------------------------------
+// out[2j,2i] = W11 in[j,i];  out[2j,2i+1] = W10 in[j,i+1] + W12 in[j,i];  out[2j+1,2i] = W01 in[j+1,i] + W21 in[j,i];
+// out[2j+1,2i+1] = W00 in[j+1,i+1] + W02 in[j+1,i] + W20 in[j,i+1] + W22 in[j,i]
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128, 3) smallconv_t2_kernel(const __grid_constant__ SmallConvParams<1, CIN, COUT> p) {
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int b = blockIdx.z / p.D, d = blockIdx.z % p.D;
+    if (i >= p.W || j >= p.H) return;
+    const int Wo = 2 * p.W;
+    const size_t plane = (size_t)p.H * p.W, oplane = 4 * plane;
+    const bool has_r = i + 1 < p.W, has_d = j + 1 < p.H;
+    float acc[4][COUT];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[k][co] = 0.0f;
+    const float* xp = p.x + (((size_t)b * CIN) * p.D + d) * plane + (size_t)j * p.W + i;
+#pragma unroll kScUnroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* q = xp + (size_t)ci * p.D * plane;
+        const float v00 = __ldg(q);
+        const float v01 = ldz(q + 1, has_r);
+        const float v10 = ldz(q + p.W, has_d);
+        const float v11 = ldz(q + p.W + 1, has_r && has_d);
+#define SCW(ky, kx) p.w[(((ky) * 3 + (kx)) * CIN + ci) * COUT + co]
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            acc[0][co] = fmaf(SCW(1, 1), v00, acc[0][co]);
+            acc[1][co] = fmaf(SCW(1, 0), v01, fmaf(SCW(1, 2), v00, acc[1][co]));
+            acc[2][co] = fmaf(SCW(0, 1), v10, fmaf(SCW(2, 1), v00, acc[2][co]));
+            acc[3][co] = fmaf(SCW(0, 0), v11, fmaf(SCW(0, 2), v10, fmaf(SCW(2, 0), v01, fmaf(SCW(2, 2), v00, acc[3][co]))));
+        }
+#undef SCW
+    }
+    const size_t o = (((size_t)b * COUT) * p.D + d) * oplane + (size_t)(2 * j) * Wo + 2 * i;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = acc[k][co] + p.bias[co];
+            if (p.relu) v[k] = fmaxf(v[k], 0.0f);
+        }
+        const size_t oc = o + (size_t)co * p.D * oplane;
+        if (p.skip != nullptr) {
+            const float2 s0 = __ldg(reinterpret_cast<const float2*>(p.skip + oc));
+            const float2 s1 = __ldg(reinterpret_cast<const float2*>(p.skip + oc + Wo));
+            v[0] += s0.x; v[1] += s0.y; v[2] += s1.x; v[3] += s1.y;
+        }
+        *reinterpret_cast<float2*>(p.y + oc) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2*>(p.y + oc + Wo) = make_float2(v[2], v[3]);
+    }
+}
+
+template <int KD, int CIN, int COUT, int MODE>
+static int launch_small(const float* x, const float* w_host, const float* bias_host, const float* skip, float* y, int B,
+                        int D, int H, int W, int relu, cudaStream_t s) {
+    static thread_local SmallConvParams<KD, CIN, COUT> p;
+    static_assert(sizeof(SmallConvParams<KD, CIN, COUT>) <= 32000, "filter bank must fit the kernel-parameter space");
+    static_assert(MODE == 0 || KD == 1, "strided / transposed layers of reg2d are (1,3,3)");
+    memcpy(p.w, w_host, sizeof(p.w));
+    memcpy(p.bias, bias_host, sizeof(p.bias));
+    p.x = x; p.skip = skip; p.y = y; p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu;
+    if ((long long)B * D > 65535) return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small: B*D too large");
+    if constexpr (MODE == 0) {
+        dim3 grid((W / 2 + 31) / 32, (H / 2 + 3) / 4, B * D);
+        smallconv_s1_kernel<KD, CIN, COUT><<<grid, 128, 0, s>>>(p);
+    } else if constexpr (MODE == 1) {
+        dim3 grid((W / 4 + 31) / 32, (H / 2 + 3) / 4, B * D);
+        smallconv_s2_kernel<CIN, COUT><<<grid, 128, 0, s>>>(p);
+    } else {
+        dim3 grid((W + 31) / 32, (H + 3) / 4, B * D);
+        smallconv_t2_kernel<CIN, COUT><<<grid, 128, 0, s>>>(p);
+    }
+    count_launch();
+    MVSTER_CHECK_LAUNCH("conv3d_small launch");
+    return MVSTER_OK;
+}
+
+}  // namespace mvster
+
+using namespace mvster;
+
+extern "C" int mvster_conv3d_small(const float* x, const float* w_host, const float* bias_host, const float* skip,
+                                   float* y, int B, int Cin, int Cout, int D, int H, int W, int kd, int mode, int relu,
+                                   void* stream) {
+    if (!x || !w_host || !bias_host || !y) return fail(MVSTER_ERR_BAD_ARG, "conv3d_small: null pointer");
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(MVSTER_ERR_BAD_ARG, "conv3d_small: non-positive dimension");
+    if (mode < 0 || mode > 2) return fail(MVSTER_ERR_BAD_ARG, "conv3d_small: mode %d not in {0,1,2}", mode);
+    if (skip != nullptr && mode != 2) return fail(MVSTER_ERR_BAD_ARG, "conv3d_small: skip is only defined for mode 2");
+    if (mode == 0 && ((H & 1) || (W & 1))) return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small: stride-1 needs even H, W");
+    if (mode == 1 && ((H & 1) || (W & 3))) return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small: stride-2 needs H%%2==0, W%%4==0");
+    if ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)skip)) % 16)
+        return fail(MVSTER_ERR_ALIGN, "conv3d_small: tensors must be 16-byte aligned");
+    DeviceGuard guard(y);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+#define SC_CASE(KD_, CI_, CO_, MODE_)                                     \
+    if (kd == KD_ && Cin == CI_ && Cout == CO_ && mode == MODE_)          \
+        return launch_small<KD_, CI_, CO_, MODE_>(x, w_host, bias_host, skip, y, B, D, H, W, relu, s);
+    SC_CASE(1, 4, 8, 0)    // reg2d.conv0, G = 4
+    SC_CASE(1, 8, 8, 0)    // reg2d.conv0, G = 8
+    SC_CASE(1, 8, 16, 1)   // reg2d.conv1
+    SC_CASE(3, 16, 16, 0)  // reg2d.conv2
+    SC_CASE(1, 16, 32, 1)  // reg2d.conv3
+    SC_CASE(1, 32, 16, 2)  // reg2d.conv9 (+ conv2 skip)
+    SC_CASE(1, 16, 8, 2)   // reg2d.conv11 (unfused form of mvster_regtail's first half)
+#undef SC_CASE
+    return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small: no kernel for Cin=%d Cout=%d kd=%d mode=%d", Cin, Cout, kd, mode);
+}

@@ -137,6 +137,8 @@ class reg2d(nn.Module):
         self.conv11 = _up3d(2 * c, c)
         self.prob = nn.Conv3d(8, 1, 1, stride=1, padding=0)  # the reference hard-codes 8 (mvs4net_utils.py:914)
         self._folded = None
+        self._fold_cache = {}
+        self.direct_convs = True  # eval-mode fused path: hand-written direct convolutions where available
 
     def _trunk(self, x):
         conv0 = self.conv0(x)
@@ -172,10 +174,59 @@ class reg2d(nn.Module):
             self._folded = (key, w, params)
         return self._folded[1], self._folded[2]
 
+    def _fold_block(self, name: str):
+        """(w_host [kd,3,3,ci,co], bias_host [co]) of a conv/deconv + BatchNorm block in eval mode, cached."""
+        blk = getattr(self, name)
+        conv, bn = (blk.conv, blk.bn) if isinstance(blk, ConvBnReLU3D) else (blk[0], blk[1])
+        key = tuple(t._version for t in (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)) \
+            + (conv.weight.data_ptr(),)
+        hit = self._fold_cache.get(name)
+        if hit is None or hit[0] != key:
+            scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+            shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+            w = conv.weight.detach().double()
+            if isinstance(conv, nn.ConvTranspose3d):          # [ci, co, kd, ky, kx]
+                w = (w * scale.view(1, -1, 1, 1, 1)).permute(2, 3, 4, 0, 1)
+            else:                                             # [co, ci, kd, ky, kx]
+                w = (w * scale.view(-1, 1, 1, 1, 1)).permute(2, 3, 4, 1, 0)
+            hit = (key, w.contiguous().float().cpu(), shift.float().cpu().contiguous())
+            self._fold_cache[name] = hit
+        return hit[1], hit[2]
+
+    def _direct(self, name: str, x, mode: int, skip=None):
+        """One block through the direct-convolution kernel when it has this layer, else through cuDNN."""
+        blk = getattr(self, name)
+        conv = blk.conv if isinstance(blk, ConvBnReLU3D) else blk[0]
+        cin, cout = conv.in_channels, conv.out_channels
+        if self.direct_convs and ops.conv3d_small_supported(cin, cout, conv.kernel_size[0], mode, x.shape[3], x.shape[4]):
+            w, bias = self._fold_block(name)
+            return ops.conv3d_small(x, w, bias, mode, True, skip)
+        y = blk(x)
+        return y if skip is None else skip + y
+
+    def _trunk_eval(self, x):
+        """``_trunk`` in eval mode: the layers at full / half resolution (conv0-conv3, conv9) run as hand-written
+        direct convolutions with BatchNorm folded and ReLU / skip add fused; the 32- and 64-channel layers at 1/4 and
+        1/8 resolution (conv4-conv7) stay on cuDNN."""
+        conv0 = self._direct("conv0", x, ops.CONV_STRIDE1)
+        conv2 = self._direct("conv2", self._direct("conv1", conv0, ops.CONV_STRIDE2), ops.CONV_STRIDE1)
+        conv4 = self.conv4(self._direct("conv3", conv2, ops.CONV_STRIDE2))
+        y = self.conv6(self.conv5(conv4))
+        y = conv4 + self.conv7(y)
+        return conv0, self._direct("conv9", y, ops.CONV_TRANSPOSED2, skip=conv2)
+
+    def forward_direct(self, x):
+        """Eval-mode logits with the direct-convolution trunk (same result as ``forward`` up to fp32 summation order);
+        used by the parity tests and when the caller wants the logits rather than the fused tail."""
+        if self.training:
+            raise RuntimeError("reg2d.forward_direct is an eval-mode path")
+        conv0, low = self._trunk_eval(x)
+        return self.prob(self._direct("conv11", low, ops.CONV_TRANSPOSED2, skip=conv0)).squeeze(1)
+
     def forward_fused_tail(self, x, depth_hypo, split_itv, inverse_depth=True, depth_mode=ops.DEPTH_ARGMAX):
         if not self.fused_tail_supported():
             raise RuntimeError("reg2d.forward_fused_tail: eval mode and base_channel == 8 required")
-        conv0, low = self._trunk(x)
+        conv0, low = self._trunk_eval(x)
         w, params = self._fold()
         return ops.regtail(low, conv0, w, params, depth_hypo, float(split_itv), bool(inverse_depth), depth_mode)
 

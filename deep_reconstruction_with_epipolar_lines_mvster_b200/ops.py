@@ -251,6 +251,49 @@ def regtail(low: torch.Tensor, skip: torch.Tensor, w_host: torch.Tensor, params_
     return attn, depth, conf, inv_min, inv_max
 
 
+CONV_STRIDE1, CONV_STRIDE2, CONV_TRANSPOSED2 = 0, 1, 2
+_SMALL_CONVS = {(4, 8, 1, 0), (8, 8, 1, 0), (8, 16, 1, 1), (16, 16, 3, 0), (16, 32, 1, 1), (32, 16, 1, 2), (16, 8, 1, 2)}
+
+
+def conv3d_small_supported(cin: int, cout: int, kd: int, mode: int, h: int, w: int) -> bool:
+    """True when ``mvster_conv3d_small`` has a kernel for this layer at input size ``h x w``."""
+    if (cin, cout, kd, mode) not in _SMALL_CONVS:
+        return False
+    if mode == CONV_STRIDE1:
+        return h % 2 == 0 and w % 2 == 0
+    if mode == CONV_STRIDE2:
+        return h % 2 == 0 and w % 4 == 0
+    return True
+
+
+def conv3d_small(x: torch.Tensor, w_host: torch.Tensor, bias_host: torch.Tensor, mode: int, relu: bool = True,
+                 skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Direct fp32 convolution of a few-channel NCDHW volume (reference ConvBnReLU3D / ConvTranspose3d+BN+ReLU blocks
+    of reg2d, mvs4net_utils.py:889-912, BatchNorm folded).  ``w_host`` [kd,3,3,Cin,Cout] and ``bias_host`` [Cout] are
+    CPU fp32 tensors (they travel as kernel parameters)."""
+    _require_cuda(x, "x")
+    x = _f32c(x, "x")
+    if x.dim() != 5 or w_host.dim() != 5 or w_host.device.type != "cpu" or bias_host.device.type != "cpu" \
+            or w_host.dtype != torch.float32 or bias_host.dtype != torch.float32 \
+            or not w_host.is_contiguous() or not bias_host.is_contiguous():
+        raise RuntimeError("conv3d_small: x must be [B,Cin,D,H,W]; w_host [kd,3,3,Cin,Cout] / bias_host [Cout] "
+                           "contiguous CPU fp32")
+    b, cin, d, h, w = x.shape
+    kd, _, _, wci, cout = w_host.shape
+    if wci != cin or bias_host.numel() != cout:
+        raise RuntimeError("conv3d_small: weight %s does not match input channels %d" % (tuple(w_host.shape), cin))
+    oh, ow = (h, w) if mode == CONV_STRIDE1 else ((h // 2, w // 2) if mode == CONV_STRIDE2 else (2 * h, 2 * w))
+    y = torch.empty((b, cout, d, oh, ow), device=x.device, dtype=torch.float32)
+    if skip is not None:
+        skip = _f32c(skip, "skip")
+        if skip.shape != y.shape:
+            raise RuntimeError("conv3d_small: skip %s does not match the output %s" % (tuple(skip.shape), tuple(y.shape)))
+    _lib.check(_lib.load().mvster_conv3d_small(
+        _ptr(x), ctypes.c_void_p(w_host.data_ptr()), ctypes.c_void_p(bias_host.data_ptr()), _ptr(skip), _ptr(y),
+        b, cin, cout, d, h, w, int(kd), int(mode), int(bool(relu)), _stream(x)))
+    return y
+
+
 def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:
     b, d, h, w = attn.shape
     g_attn = None if g_attn is None else _f32c(g_attn, "grad attn")

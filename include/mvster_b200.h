@@ -141,6 +141,21 @@ int mvster_tail(const float* logits, const float* hypo, float split_itv, int dep
 int mvster_regtail(const float* low, const float* skip, const float* w, const float* params, const float* hypo,
                    float split_itv, int depth_mode, float* attn, float* depth, float* conf, float* inv_min,
                    float* inv_max, int B, int D, int H, int W, void* stream);
+/* ---- direct fp32 convolutions for reg2d's high-resolution, few-channel layers ---------
+ * Replaces, in eval mode, ConvBnReLU3D / (ConvTranspose3d + BatchNorm3d + ReLU) blocks of reg2d
+ * (models/mvs4net_utils.py:889-912; building blocks :123-130) for the layers whose whole filter bank fits in the
+ * kernel-parameter constant bank.  BatchNorm is folded by the caller: y = relu(conv(x, w) + bias) [+ skip].
+ *   x     dev  [B, Cin, D, H, W] fp32 NCDHW;   y dev [B, Cout, D, H', W']
+ *   w     HOST [kd, 3, 3, Cin, Cout]  ([kd][ky][kx][ci][co]);   bias HOST [Cout]
+ *   mode  0: Conv3d k=(kd,3,3) stride 1 padding (kd/2,1,1), H'=H W'=W            (H, W even)
+ *         1: Conv3d k=(1,3,3) stride (1,2,2) padding (0,1,1), H'=H/2 W'=W/2       (H even, W % 4 == 0)
+ *         2: ConvTranspose3d k=(1,3,3) stride (1,2,2) padding (0,1,1) output_padding (0,1,1), H'=2H W'=2W;
+ *            skip (dev, [B,Cout,D,2H,2W], nullable) is added AFTER the ReLU (reg2d: x = conv2 + conv9(x))
+ * Compiled (Cin, Cout, kd, mode): (4,8,1,0) (8,8,1,0) (8,16,1,1) (16,16,3,0) (16,32,1,1) (32,16,1,2) (16,8,1,2);
+ * anything else returns MVSTER_ERR_UNSUPPORTED and the caller keeps the layer on cuDNN.
+ */
+int mvster_conv3d_small(const float* x, const float* w, const float* bias, const float* skip, float* y, int B, int Cin,
+                        int Cout, int D, int H, int W, int kd, int mode, int relu, void* stream);
 /* backward of the tail w.r.t. the logits: softmax backward of g_attn (+ the regression term of g_depth when
  * depth_mode == MVSTER_DEPTH_REGRESS); g_attn / g_depth may be NULL (treated as zero) */
 int mvster_tail_bwd(const float* attn, const float* hypo, const float* depth, const float* g_attn,

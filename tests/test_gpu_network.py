@@ -154,3 +154,61 @@ def test_mvs4net_fused_and_unfused_paths_agree(model):
     assert (a["attn_weight"] - b["attn_weight"]).abs().max().item() < 1e-4
     same = (outs[0]["stage4"]["depth"] == outs[1]["stage4"]["depth"]).float().mean().item()
     assert same > 0.98, same
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# direct few-channel convolutions (mvster_conv3d_small)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,kd,mode,d,h,w", [
+    (4, 8, 1, 0, 4, 10, 12), (8, 8, 1, 0, 8, 6, 66), (8, 16, 1, 1, 4, 12, 72), (16, 16, 3, 0, 4, 8, 10),
+    (16, 16, 3, 0, 1, 4, 4), (16, 32, 1, 1, 8, 6, 8), (32, 16, 1, 2, 4, 5, 7), (16, 8, 1, 2, 8, 3, 35)])
+def test_conv3d_small_matches_float64_torch(cin, cout, kd, mode, d, h, w):
+    """Each compiled layer shape against torch's own convolution evaluated in float64 on the CPU (the reference's op,
+    mvs4net_utils.py:123-130 / :899-912, with BatchNorm folded), including borders, odd tile counts and the skip add."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(cin * 100 + cout + mode)
+    b = 2
+    x = rng.normal(0, 1, (b, cin, d, h, w)).astype(np.float32)
+    wt = rng.normal(0, 0.2, (kd, 3, 3, cin, cout)).astype(np.float32)          # [kd][ky][kx][ci][co]
+    bias = rng.normal(0, 0.3, cout).astype(np.float32)
+    xd, wd = torch.from_numpy(x).double(), torch.from_numpy(wt).double()
+    skip = None
+    if mode == 0:
+        ref = F.conv3d(xd, wd.permute(4, 3, 0, 1, 2), padding=(kd // 2, 1, 1))
+    elif mode == 1:
+        ref = F.conv3d(xd, wd.permute(4, 3, 0, 1, 2), stride=(1, 2, 2), padding=(0, 1, 1))
+    else:
+        ref = F.conv_transpose3d(xd, wd.permute(3, 4, 0, 1, 2), stride=(1, 2, 2), padding=(0, 1, 1),
+                                 output_padding=(0, 1, 1))
+        skip = rng.normal(0, 1, tuple(ref.shape)).astype(np.float32)
+    ref = torch.relu(ref + torch.from_numpy(bias).double().view(1, -1, 1, 1, 1))
+    if skip is not None:
+        ref = ref + torch.from_numpy(skip).double()
+    got = ops.conv3d_small(torch.from_numpy(x).to(DEV), torch.from_numpy(wt), torch.from_numpy(bias), mode, True,
+                           None if skip is None else torch.from_numpy(skip).to(DEV))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert (got.cpu().double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv3d_small_rejects_unsupported_layers():
+    x = torch.zeros((1, 5, 4, 8, 8), device=DEV)
+    with pytest.raises(RuntimeError, match="no kernel"):
+        ops.conv3d_small(x, torch.zeros((1, 3, 3, 5, 8)), torch.zeros(8), 0)
+    with pytest.raises(RuntimeError, match="even"):
+        ops.conv3d_small(torch.zeros((1, 4, 4, 7, 8), device=DEV), torch.zeros((1, 3, 3, 4, 8)), torch.zeros(8), 0)
+    assert not ops.conv3d_small_supported(64, 64, 3, 0, 8, 8) and ops.conv3d_small_supported(16, 16, 3, 0, 8, 8)
+
+
+def test_reg2d_direct_trunk_matches_reference_golden(golden, model):
+    """reg2d with conv0-conv3, conv9, conv11 on the hand-written kernels (BatchNorm folded) against the unmodified
+    reference's logits on its own volumes, all four stages."""
+    g = golden("network")
+    for s in range(4):
+        vol = torch.from_numpy(g["s%d_volume" % (s + 1)]).to(DEV)
+        with torch.no_grad():
+            logits = model.reg[s].forward_direct(vol)
+            cudnn = model.reg[s](vol)
+        ref = g["s%d_logits" % (s + 1)]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert np.abs(logits.cpu().numpy() - ref).max() < 5e-5 * scale, "stage %d" % (s + 1)
+        assert (logits - cudnn).abs().max().item() < 5e-5 * scale
