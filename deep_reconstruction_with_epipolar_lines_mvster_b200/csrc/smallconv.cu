@@ -30,6 +30,7 @@ struct SmallConvParams {
     float* y;
     int B, D, H, W;  // INPUT height / width
     int relu;
+    int co_total, co_off;  // the COUT channels computed here are channels co_off .. co_off+COUT-1 of a co_total-channel y
 };
 
 __device__ __forceinline__ float ldz(const float* p, bool ok) { return ok ? __ldg(p) : 0.0f; }
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(128, 3) smallconv_s1_kernel(const __grid_const
                     }
         }
     }
-    float* yp = p.y + (((size_t)b * COUT) * p.D + d) * plane + (size_t)y0 * W + x0;
+    float* yp = p.y + (((size_t)b * p.co_total + p.co_off) * p.D + d) * plane + (size_t)y0 * W + x0;
 #pragma unroll
     for (int co = 0; co < COUT; ++co) {
         float v[2][2];
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(128, 3) smallconv_s2_kernel(const __grid_const
                     acc[1][co] = fmaf(wv, in[ky][kx + 2], acc[1][co]);
                 }
     }
-    float* yp = p.y + (((size_t)b * COUT) * p.D + d) * oplane + (size_t)oy * Wo + 2 * i;
+    float* yp = p.y + (((size_t)b * p.co_total + p.co_off) * p.D + d) * oplane + (size_t)oy * Wo + 2 * i;
 #pragma unroll
     for (int co = 0; co < COUT; ++co) {
         float v0 = acc[0][co] + p.bias[co], v1 = acc[1][co] + p.bias[co];
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(128, 3) smallconv_t2_kernel(const __grid_const
         }
 #undef SCW
     }
-    const size_t o = (((size_t)b * COUT) * p.D + d) * oplane + (size_t)(2 * j) * Wo + 2 * i;
+    const size_t o = (((size_t)b * p.co_total + p.co_off) * p.D + d) * oplane + (size_t)(2 * j) * Wo + 2 * i;
 #pragma unroll
     for (int co = 0; co < COUT; ++co) {
         float v[4];
@@ -215,15 +216,93 @@ __global__ void __launch_bounds__(128, 3) smallconv_t2_kernel(const __grid_const
     }
 }
 
+// ---- 5x5, stride 2, padding 2 (FPN4 down-sampling layers, models/mvs4net_utils.py:438,444; D = 1) -------------------
+template <int CIN, int COUT>
+struct Conv5Params {
+    float w[25 * CIN * COUT];  // [ky][kx][ci][co]
+    float bias[COUT];
+    const float* x;
+    float* y;
+    int B, H, W, relu, co_total, co_off;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128, 3) conv5s2_kernel(const __grid_constant__ Conv5Params<CIN, COUT> p) {
+    const int Ho = p.H / 2, Wo = p.W / 2;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (2 * i >= Wo || oy >= Ho) return;
+    const int H = p.H, W = p.W;
+    const int xi = 4 * i;  // outputs 2i, 2i+1 read input columns xi-2 .. xi+4
+    const size_t plane = (size_t)H * W, oplane = (size_t)Ho * Wo;
+    float acc[2][COUT];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[c][co] = 0.0f;
+    bool vy[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) vy[r] = (unsigned)(2 * oy - 2 + r) < (unsigned)H;
+    const bool vl = xi > 0, vr = xi + 4 < W;
+    const float* xp = p.x + ((size_t)b * CIN) * plane + (size_t)(2 * oy - 2) * W + xi;
+#pragma unroll 1
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* q = xp + (size_t)ci * plane;
+        float in[5][7];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const float* qr = q + (size_t)r * W;
+            const float2 l = ldz2(qr - 2, vy[r] && vl);
+            const float4 m = ldz4(qr, vy[r]);
+            in[r][0] = l.x; in[r][1] = l.y; in[r][2] = m.x; in[r][3] = m.y; in[r][4] = m.z; in[r][5] = m.w;
+            in[r][6] = ldz(qr + 4, vy[r] && vr);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float wv = p.w[((ky * 5 + kx) * CIN + ci) * COUT + co];
+                    acc[0][co] = fmaf(wv, in[ky][kx], acc[0][co]);
+                    acc[1][co] = fmaf(wv, in[ky][kx + 2], acc[1][co]);
+                }
+    }
+    float* yp = p.y + ((size_t)b * p.co_total + p.co_off) * oplane + (size_t)oy * Wo + 2 * i;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        float v0 = acc[0][co] + p.bias[co], v1 = acc[1][co] + p.bias[co];
+        if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+        *reinterpret_cast<float2*>(yp + (size_t)co * oplane) = make_float2(v0, v1);
+    }
+}
+
+template <int CIN, int COUT>
+static int launch_conv5(const float* x, const float* w_host, const float* bias_host, float* y, int B, int H, int W,
+                        int relu, int co_total, int co_off, cudaStream_t s) {
+    static thread_local Conv5Params<CIN, COUT> p;
+    static_assert(sizeof(Conv5Params<CIN, COUT>) <= 32000, "filter bank must fit the kernel-parameter space");
+    memcpy(p.w, w_host, sizeof(p.w));
+    memcpy(p.bias, bias_host, sizeof(p.bias));
+    p.x = x; p.y = y; p.B = B; p.H = H; p.W = W; p.relu = relu; p.co_total = co_total; p.co_off = co_off;
+    if (B > 65535) return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_small: B too large");
+    dim3 grid((W / 4 + 31) / 32, (H / 2 + 3) / 4, B);
+    conv5s2_kernel<CIN, COUT><<<grid, 128, 0, s>>>(p);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("conv2d_small launch");
+    return MVSTER_OK;
+}
+
 template <int KD, int CIN, int COUT, int MODE>
 static int launch_small(const float* x, const float* w_host, const float* bias_host, const float* skip, float* y, int B,
-                        int D, int H, int W, int relu, cudaStream_t s) {
+                        int D, int H, int W, int relu, cudaStream_t s, int co_total = COUT, int co_off = 0) {
     static thread_local SmallConvParams<KD, CIN, COUT> p;
     static_assert(sizeof(SmallConvParams<KD, CIN, COUT>) <= 32000, "filter bank must fit the kernel-parameter space");
     static_assert(MODE == 0 || KD == 1, "strided / transposed layers of reg2d are (1,3,3)");
     memcpy(p.w, w_host, sizeof(p.w));
     memcpy(p.bias, bias_host, sizeof(p.bias));
     p.x = x; p.skip = skip; p.y = y; p.B = B; p.D = D; p.H = H; p.W = W; p.relu = relu;
+    p.co_total = co_total; p.co_off = co_off;
     if ((long long)B * D > 65535) return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small: B*D too large");
     if constexpr (MODE == 0) {
         dim3 grid((W / 2 + 31) / 32, (H / 2 + 3) / 4, B * D);
@@ -270,4 +349,38 @@ extern "C" int mvster_conv3d_small(const float* x, const float* w_host, const fl
     SC_CASE(1, 16, 8, 2)   // reg2d.conv11 (unfused form of mvster_regtail's first half)
 #undef SC_CASE
     return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small: no kernel for Cin=%d Cout=%d kd=%d mode=%d", Cin, Cout, kd, mode);
+}
+
+// 2-D layers of FPN4 (models/mvs4net_utils.py:431-449, eval mode, BatchNorm folded): NCHW planar fp32 in and out.
+// A layer with more output channels than one filter-bank slice holds is launched once per slice of `Cout` channels
+// (co_off .. co_off+Cout-1 of a Cout_total-channel output).
+extern "C" int mvster_conv2d_small(const float* x, const float* w_host, const float* bias_host, float* y, int B, int Cin,
+                                   int Cout, int Cout_total, int co_off, int H, int W, int ksize, int stride, int relu,
+                                   void* stream) {
+    if (!x || !w_host || !bias_host || !y) return fail(MVSTER_ERR_BAD_ARG, "conv2d_small: null pointer");
+    if (B <= 0 || H <= 0 || W <= 0 || Cout <= 0 || co_off < 0 || co_off + Cout > Cout_total)
+        return fail(MVSTER_ERR_BAD_ARG, "conv2d_small: bad dimension / channel slice");
+    if (!((ksize == 3 && stride == 1) || (ksize == 5 && stride == 2)))
+        return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_small: only 3x3 stride 1 and 5x5 stride 2 are built");
+    if (stride == 1 && ((H & 1) || (W & 1))) return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_small: 3x3 needs even H, W");
+    if (stride == 2 && ((H & 1) || (W & 3))) return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_small: 5x5/2 needs H%%2==0, W%%4==0");
+    if ((((uintptr_t)x) | ((uintptr_t)y)) % 16) return fail(MVSTER_ERR_ALIGN, "conv2d_small: tensors must be 16-byte aligned");
+    DeviceGuard guard(y);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+#define C3_CASE(CI_, CO_)                                    \
+    if (ksize == 3 && Cin == CI_ && Cout == CO_)             \
+        return launch_small<1, CI_, CO_, 0>(x, w_host, bias_host, nullptr, y, B, 1, H, W, relu, s, Cout_total, co_off);
+#define C5_CASE(CI_, CO_)                                    \
+    if (ksize == 5 && Cin == CI_ && Cout == CO_)             \
+        return launch_conv5<CI_, CO_>(x, w_host, bias_host, y, B, H, W, relu, Cout_total, co_off, s);
+    C3_CASE(3, 8)     // FPN4.conv0.0
+    C3_CASE(8, 8)     // FPN4.conv0.1
+    C3_CASE(16, 16)   // FPN4.conv1.1 / conv1.2
+    C3_CASE(32, 16)   // FPN4.conv2.1 / conv2.2, two slices of 16 output channels
+    C5_CASE(8, 16)    // FPN4.conv1.0
+    C5_CASE(16, 16)   // FPN4.conv2.0, two slices of 16 output channels
+#undef C3_CASE
+#undef C5_CASE
+    return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_small: no kernel for Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
 }

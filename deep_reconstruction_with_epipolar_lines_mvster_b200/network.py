@@ -70,6 +70,72 @@ class FPN4(nn.Module):
         self.out3 = nn.Conv2d(top, 2 * c, 3, padding=1, bias=False)
         self.out4 = nn.Conv2d(top, c, 3, padding=1, bias=False)
         self.out_channels = [8 * c, 4 * c, 2 * c, c]
+        self.direct_convs = True  # eval: hand-written kernels for the encoder and the two finest top-down levels
+        self._fold_cache = {}
+
+    # ---- eval-mode path on the hand-written kernels ---------------------------------------------------------------
+    def _folded(self, blk: "Conv2d", tag: str):
+        """BatchNorm-folded weight of a Conv2d block as per-launch slices ``[k,k,ci,cs]`` + bias slices (host)."""
+        conv, bn = blk.conv, blk.bn
+        key = tuple(t._version for t in (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)) \
+            + (conv.weight.data_ptr(),)
+        hit = self._fold_cache.get(tag)
+        if hit is None or hit[0] != key:
+            scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+            shift = (bn.bias.detach().double() - bn.running_mean.detach().double() * scale).float().cpu()
+            w = (conv.weight.detach().double() * scale.view(-1, 1, 1, 1)).permute(2, 3, 1, 0).float().cpu()  # [ky,kx,ci,co]
+            cs = ops._CONV2D_SLICE[(conv.in_channels, conv.kernel_size[0])]
+            n = conv.out_channels // cs
+            hit = (key, [w[..., i * cs:(i + 1) * cs].contiguous() for i in range(n)],
+                   [shift[i * cs:(i + 1) * cs].contiguous() for i in range(n)])
+            self._fold_cache[tag] = hit
+        return hit[1], hit[2]
+
+    def _topdown_weights(self, out_conv: nn.Conv2d, inner: nn.Conv2d, tag: str):
+        key = (out_conv.weight._version, inner.weight._version, inner.bias._version, out_conv.weight.data_ptr())
+        hit = self._fold_cache.get(tag)
+        if hit is None or hit[0] != key:
+            w = out_conv.weight.detach().permute(2, 3, 1, 0).float().cpu()                      # [ky,kx,c64,co]
+            slices = [w[..., i * 8:(i + 1) * 8].contiguous() for i in range(out_conv.out_channels // 8)]
+            w_in = inner.weight.detach()[:, :, 0, 0].t().contiguous().float().cpu()             # [cl, c64]
+            hit = (key, slices, w_in, inner.bias.detach().float().cpu().contiguous())
+            self._fold_cache[tag] = hit
+        return hit[1], hit[2], hit[3]
+
+    def direct_supported(self, x) -> bool:
+        return (self.direct_convs and not self.training and self.base_channels == 8 and x.is_cuda
+                and x.shape[2] % 8 == 0 and x.shape[3] % 16 == 0)
+
+    def _block(self, blk: "Conv2d", tag: str, x):
+        k, s = blk.conv.kernel_size[0], blk.conv.stride[0]
+        if ops.conv2d_small_supported(blk.conv.in_channels, blk.conv.out_channels, k, s, x.shape[2], x.shape[3]):
+            w, b = self._folded(blk, tag)
+            return ops.conv2d_small(x, w, b, k, s, True)
+        return blk(x)
+
+    def forward_direct(self, x) -> Dict[str, torch.Tensor]:
+        """Eval-mode FPN4 on the B200 kernels: encoder levels 0-2 as direct convolutions (BatchNorm folded), level 3
+        and the coarse top-down steps on cuDNN, the two finest top-down steps fused with their output convolutions
+        (``ops.fpn_topdown``).  Every output is NHWC in memory (``channels_last`` strides), ready for K1."""
+        x = x.contiguous()
+        c0 = self._block(self.conv0[1], "c01", self._block(self.conv0[0], "c00", x))
+        c1 = c0
+        for i, blk in enumerate(self.conv1):
+            c1 = self._block(blk, "c1%d" % i, c1)
+        c2 = c1
+        for i, blk in enumerate(self.conv2):
+            c2 = self._block(blk, "c2%d" % i, c2)
+        top = self.conv3(c2)
+        out = {"stage1": self.out1(top).contiguous(memory_format=torch.channels_last)}
+        intra2 = self._up(top) + self.inner1(c2)
+        out["stage2"] = self.out2(intra2).contiguous(memory_format=torch.channels_last)
+        w3, wi3, bi3 = self._topdown_weights(self.out3, self.inner2, "td3")
+        feat3, intra3 = ops.fpn_topdown(intra2, c1, w3, wi3, bi3, want_intra=True)
+        w4, wi4, bi4 = self._topdown_weights(self.out4, self.inner3, "td4")
+        feat4, _ = ops.fpn_topdown(intra3, c0, w4, wi4, bi4, want_intra=False)
+        out["stage3"] = feat3.permute(0, 3, 1, 2)
+        out["stage4"] = feat4.permute(0, 3, 1, 2)
+        return out
 
     @staticmethod
     def _up(x):
@@ -279,8 +345,11 @@ class MVS4net(nn.Module):
         if self.training:
             return [self.feature(img.contiguous(memory_format=torch.channels_last)) for img in imgs]
         b = imgs[0].shape[0]
-        stacked = torch.cat(list(imgs), 0).contiguous(memory_format=torch.channels_last)
-        out = self.feature(stacked)
+        stacked = torch.cat(list(imgs), 0)
+        if self.feature.direct_supported(stacked) and not torch.is_grad_enabled():
+            out = self.feature.forward_direct(stacked)
+        else:
+            out = self.feature(stacked.contiguous(memory_format=torch.channels_last))
         return [{k: v[i * b:(i + 1) * b] for k, v in out.items()} for i in range(n)]
 
     # ---- forward ------------------------------------------------------------------------------------------------------

@@ -294,6 +294,71 @@ def conv3d_small(x: torch.Tensor, w_host: torch.Tensor, bias_host: torch.Tensor,
     return y
 
 
+_CONV2D_SLICE = {(3, 3): 8, (8, 3): 8, (16, 3): 16, (32, 3): 16, (8, 5): 16, (16, 5): 16}  # (Cin, k) -> Cout per launch
+
+
+def conv2d_small_supported(cin: int, cout: int, ksize: int, stride: int, h: int, w: int) -> bool:
+    cs = _CONV2D_SLICE.get((cin, ksize))
+    if cs is None or cout % cs or (ksize, stride) not in ((3, 1), (5, 2)):
+        return False
+    return (h % 2 == 0 and w % 2 == 0) if stride == 1 else (h % 2 == 0 and w % 4 == 0)
+
+
+def conv2d_small(x: torch.Tensor, w_slices: Sequence[torch.Tensor], b_slices: Sequence[torch.Tensor], ksize: int,
+                 stride: int, relu: bool = True) -> torch.Tensor:
+    """Conv2d + folded BatchNorm + ReLU of an FPN4 encoder block (mvs4net_utils.py:231-258) on NCHW planar fp32.
+    ``w_slices[i]`` [k,k,Cin,cs] / ``b_slices[i]`` [cs] are CPU fp32 tensors, one per slice of ``cs`` output channels."""
+    _require_cuda(x, "x")
+    x = _f32c(x, "x")
+    b, cin, h, w = x.shape
+    cs = w_slices[0].shape[3]
+    cout = cs * len(w_slices)
+    oh, ow = (h, w) if stride == 1 else (h // 2, w // 2)
+    y = torch.empty((b, cout, oh, ow), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    for i, (ws, bs) in enumerate(zip(w_slices, b_slices)):
+        if ws.device.type != "cpu" or ws.dtype != torch.float32 or not ws.is_contiguous() \
+                or tuple(ws.shape) != (ksize, ksize, cin, cs) or bs.numel() != cs or not bs.is_contiguous():
+            raise RuntimeError("conv2d_small: weight slices must be contiguous CPU fp32 [k,k,Cin,cs]")
+        _lib.check(lib.mvster_conv2d_small(_ptr(x), ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(bs.data_ptr()),
+                                           _ptr(y), b, cin, cs, cout, i * cs, h, w, int(ksize), int(stride),
+                                           int(bool(relu)), _stream(x)))
+    return y
+
+
+def fpn_topdown(prev: torch.Tensor, lat: torch.Tensor, w_out_slices: Sequence[torch.Tensor], w_in_host: torch.Tensor,
+                b_in_host: torch.Tensor, want_intra: bool):
+    """One FPN4 top-down level (mvs4net_utils.py:488-495): ``intra = up2(prev) + inner(lat); feat = out_conv(intra)``.
+    ``prev`` [B,64,H/2,W/2], ``lat`` [B,Clat,H,W] planar CUDA fp32; ``w_out_slices[i]`` [3,3,64,8] CPU.
+    Returns ``(feat NHWC [B,H,W,8*len(slices)], intra [B,64,H,W] or None)``; ``intra`` is materialised only when asked
+    for or when a second output-channel slice has to reload it."""
+    _require_cuda(prev, "prev")
+    prev, lat = _f32c(prev, "prev"), _f32c(lat, "lat")
+    b, clat, h, w = lat.shape
+    if tuple(prev.shape) != (b, 64, h // 2, w // 2) or h % 2 or w % 2:
+        raise RuntimeError("fpn_topdown: prev %s does not match lat %s" % (tuple(prev.shape), tuple(lat.shape)))
+    ns = len(w_out_slices)
+    cout = 8 * ns
+    feat = torch.empty((b, h, w, cout), device=lat.device, dtype=torch.float32)
+    intra = torch.empty((b, 64, h, w), device=lat.device, dtype=torch.float32) if (want_intra or ns > 1) else None
+    lib = _lib.load()
+    for t in (w_in_host, b_in_host) + tuple(w_out_slices):
+        if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("fpn_topdown: weights must be contiguous CPU fp32 tensors")
+    if tuple(w_in_host.shape) != (clat, 64) or b_in_host.numel() != 64:
+        raise RuntimeError("fpn_topdown: w_in must be [Clat,64], b_in [64]")
+    for i, ws in enumerate(w_out_slices):
+        if tuple(ws.shape) != (3, 3, 64, 8):
+            raise RuntimeError("fpn_topdown: output-conv slices must be [3,3,64,8]")
+        first = i == 0
+        _lib.check(lib.mvster_fpn_topdown(
+            _ptr(prev) if first else None, _ptr(lat) if first else None, None if first else _ptr(intra),
+            _ptr(intra) if first else None, _ptr(feat), ctypes.c_void_p(ws.data_ptr()),
+            ctypes.c_void_p(w_in_host.data_ptr()), ctypes.c_void_p(b_in_host.data_ptr()), b, clat, 8, cout, 8 * i, h, w,
+            _stream(lat)))
+    return feat, intra
+
+
 def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:
     b, d, h, w = attn.shape
     g_attn = None if g_attn is None else _f32c(g_attn, "grad attn")

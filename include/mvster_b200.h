@@ -156,6 +156,29 @@ int mvster_regtail(const float* low, const float* skip, const float* w, const fl
  */
 int mvster_conv3d_small(const float* x, const float* w, const float* bias, const float* skip, float* y, int B, int Cin,
                         int Cout, int D, int H, int W, int kd, int mode, int relu, void* stream);
+/* ---- FPN4: few-channel 2-D convolutions and the fused top-down step ----------------------
+ * mvster_conv2d_small: Conv2d + BatchNorm2d (folded) + ReLU blocks of FPN4's encoder (models/mvs4net_utils.py:431-449,
+ * building block :231-258), NCHW planar fp32.  3x3 stride 1 padding 1 (H, W even) or 5x5 stride 2 padding 2 (H even,
+ * W % 4 == 0).  One launch computes output channels co_off .. co_off+Cout-1 of a Cout_total-channel y:
+ *   x dev [B,Cin,H,W];  y dev [B,Cout_total,H',W'];  w HOST [k,k,Cin,Cout] (slice);  bias HOST [Cout]
+ * Compiled (Cin, Cout, k): (3,8,3) (8,8,3) (16,16,3) (32,16,3) (8,16,5) (16,16,5).
+ */
+int mvster_conv2d_small(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                        int Cout_total, int co_off, int H, int W, int ksize, int stride, int relu, void* stream);
+/* mvster_fpn_topdown: one pyramid level of FPN4.forward (models/mvs4net_utils.py:488-495),
+ *     intra = interpolate(prev, x2, bilinear, align_corners=True) + inner(lat);  feat = out_conv(intra)
+ * with the 64-channel intra tile kept in shared memory; feat is written NHWC (what mvster_epi_fwd reads).
+ *   prev      dev  [B,64,H/2,W/2] planar (nullable when intra_in is given)
+ *   lat       dev  [B,Clat,H,W]   planar encoder map (nullable when intra_in is given)
+ *   intra_in  dev  [B,64,H,W]     nullable: reload the tile instead of computing it (second output-channel slice)
+ *   intra_out dev  [B,64,H,W]     nullable: store intra (needed by the next finer level)
+ *   feat      dev  [B,H,W,Cout_total] NHWC; this launch writes channels co_off .. co_off+Cout-1
+ *   w_out HOST [3,3,64,Cout] (slice of out_conv.weight as [ky][kx][c64][co]); w_in HOST [Clat,64]; b_in HOST [64]
+ * Compiled (Clat, Cout): (8,8), (16,8).  H, W even.
+ */
+int mvster_fpn_topdown(const float* prev, const float* lat, const float* intra_in, float* intra_out, float* feat,
+                       const float* w_out, const float* w_in, const float* b_in, int B, int Clat, int Cout,
+                       int Cout_total, int co_off, int H, int W, void* stream);
 /* backward of the tail w.r.t. the logits: softmax backward of g_attn (+ the regression term of g_depth when
  * depth_mode == MVSTER_DEPTH_REGRESS); g_attn / g_depth may be NULL (treated as zero) */
 int mvster_tail_bwd(const float* attn, const float* hypo, const float* depth, const float* g_attn,

@@ -258,6 +258,7 @@ def bench_network(args, dev):
     # where the time goes on the B200 path (fused, fp32)
     torch.backends.cudnn.allow_tf32 = False
     model.stagenet, model.fuse_regnet_tail = fused_stagenet, True
+    model.__dict__.pop("extract_features", None)
     with torch.no_grad():
         res["fpn_ms"] = timed(lambda: model.extract_features(imgs), its)
         vol = torch.randn((b, 4, 4, h0, w0), device=dev)

@@ -212,3 +212,66 @@ def test_reg2d_direct_trunk_matches_reference_golden(golden, model):
         scale = max(1.0, float(np.abs(ref).max()))
         assert np.abs(logits.cpu().numpy() - ref).max() < 5e-5 * scale, "stage %d" % (s + 1)
         assert (logits - cudnn).abs().max().item() < 5e-5 * scale
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# FPN4 on the hand-written kernels (mvster_conv2d_small, mvster_fpn_topdown)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,k,stride,h,w", [(3, 8, 3, 1, 10, 14), (8, 8, 3, 1, 6, 66), (16, 16, 3, 1, 8, 8),
+                                                  (32, 32, 3, 1, 6, 10), (8, 16, 5, 2, 12, 72), (16, 32, 5, 2, 10, 8)])
+def test_conv2d_small_matches_float64_torch(cin, cout, k, stride, h, w):
+    import torch.nn.functional as F
+    rng = np.random.RandomState(cin * 10 + cout + k)
+    x = rng.normal(0, 1, (2, cin, h, w)).astype(np.float32)
+    wt = rng.normal(0, 0.2, (k, k, cin, cout)).astype(np.float32)
+    bias = rng.normal(0, 0.3, cout).astype(np.float32)
+    ref = F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(wt).double().permute(3, 2, 0, 1), stride=stride,
+                   padding=k // 2)
+    ref = torch.relu(ref + torch.from_numpy(bias).double().view(1, -1, 1, 1))
+    cs = ops._CONV2D_SLICE[(cin, k)]
+    ws = [torch.from_numpy(np.ascontiguousarray(wt[..., i * cs:(i + 1) * cs])) for i in range(cout // cs)]
+    bs = [torch.from_numpy(np.ascontiguousarray(bias[i * cs:(i + 1) * cs])) for i in range(cout // cs)]
+    got = ops.conv2d_small(torch.from_numpy(x).to(DEV), ws, bs, k, stride, True)
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert (got.cpu().double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("clat,cout,h,w,want_intra", [(8, 8, 16, 64, False), (16, 16, 12, 36, True), (8, 8, 10, 70, True)])
+def test_fpn_topdown_matches_float64_torch(clat, cout, h, w, want_intra):
+    """up2(prev, bilinear, align_corners=True) + inner(lat) -> 3x3 out conv, against the same ops in float64 (tile
+    borders, image borders, partial tiles, two output-channel slices, intra store / reload)."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(clat + cout + h)
+    prev = rng.normal(0, 1, (2, 64, h // 2, w // 2)).astype(np.float32)
+    lat = rng.normal(0, 1, (2, clat, h, w)).astype(np.float32)
+    w_out = rng.normal(0, 0.05, (cout, 64, 3, 3)).astype(np.float32)
+    w_in = rng.normal(0, 0.3, (64, clat, 1, 1)).astype(np.float32)
+    b_in = rng.normal(0, 0.2, 64).astype(np.float32)
+    pd, ld = torch.from_numpy(prev).double(), torch.from_numpy(lat).double()
+    intra = F.interpolate(pd, scale_factor=2, mode="bilinear", align_corners=True) + \
+        F.conv2d(ld, torch.from_numpy(w_in).double(), torch.from_numpy(b_in).double())
+    ref = F.conv2d(intra, torch.from_numpy(w_out).double(), padding=1)
+    wo = torch.from_numpy(w_out).permute(2, 3, 1, 0)
+    slices = [wo[..., i * 8:(i + 1) * 8].contiguous() for i in range(cout // 8)]
+    feat, got_intra = ops.fpn_topdown(torch.from_numpy(prev).to(DEV), torch.from_numpy(lat).to(DEV), slices,
+                                      torch.from_numpy(w_in[:, :, 0, 0].T.copy()), torch.from_numpy(b_in), want_intra)
+    assert tuple(feat.shape) == (2, h, w, cout)
+    err = (feat.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+    if want_intra:
+        assert (got_intra.cpu().double() - intra).abs().max().item() < 1e-5 * max(1.0, intra.abs().max().item())
+    else:
+        assert got_intra is None
+
+
+def test_fpn4_direct_path_matches_reference_golden(golden, model):
+    g = golden("network")
+    x = torch.from_numpy(g["imgs"][1]).to(DEV)
+    assert model.feature.direct_supported(x)
+    with torch.no_grad():
+        out = model.feature.forward_direct(x)
+    for k in ("stage1", "stage2", "stage3", "stage4"):
+        ref = g["fpn_view1_" + k]
+        assert tuple(out[k].shape) == ref.shape
+        assert out[k].is_contiguous(memory_format=torch.channels_last)
+        assert np.abs(out[k].cpu().numpy() - ref).max() < 5e-5 * max(1.0, float(np.abs(ref).max())), k
