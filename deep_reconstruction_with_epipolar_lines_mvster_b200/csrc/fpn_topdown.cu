@@ -38,73 +38,13 @@ struct TopDownParams {
     float sy, sx;           // align_corners=True source scale (Hl-1)/(H-1), (Wl-1)/(W-1)
 };
 
-template <int CL, int CO>
-__global__ void __launch_bounds__(128, 2) fpn_topdown_kernel(const __grid_constant__ TopDownParams<CL, CO> p) {
-    extern __shared__ float tile[];  // [64][kTdHH][kTdRS]
-    const int tid = threadIdx.x;
-    const int b = blockIdx.z;
-    const int tx0 = blockIdx.x * kTdTW, ty0 = blockIdx.y * kTdTH;
-    const int H = p.H, W = p.W, Hl = H / 2, Wl = W / 2;
-    const size_t plane = (size_t)H * W, lplane = (size_t)Hl * Wl;
-
-    // ---- phase 1: the 64-channel intra tile (+ halo) -> shared memory ------------------------------------------------
-    for (int hp = tid; hp < kTdHH * kTdHW; hp += 128) {
-        const int ry = hp / kTdHW, rx = hp - ry * kTdHW;
-        const int gy = ty0 - 1 + ry, gx = tx0 - 1 + rx;
-        float* ts = tile + ry * kTdRS + rx;
-        const bool inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-        if (!inside) {  // zero padding of the 3x3 output convolution
-#pragma unroll 8
-            for (int c = 0; c < 64; ++c) ts[c * (kTdHH * kTdRS)] = 0.0f;
-            continue;
-        }
-        const size_t go = (size_t)gy * W + gx;
-        if (p.intra_in != nullptr) {
-            const float* ip = p.intra_in + (size_t)b * 64 * plane + go;
-#pragma unroll 8
-            for (int c = 0; c < 64; ++c) ts[c * (kTdHH * kTdRS)] = __ldg(ip + (size_t)c * plane);
-            continue;
-        }
-        // bilinear x2, align_corners=True, with ATen's arithmetic (upsample_bilinear2d: source = scale * dst)
-        const float fy = p.sy * (float)gy, fx = p.sx * (float)gx;
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = y0 + (y0 < Hl - 1), x1 = x0 + (x0 < Wl - 1);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
-        const float hy = 1.0f - ly, hx = 1.0f - lx;
-        const float* pp = p.prev + (size_t)b * 64 * lplane;
-        const size_t o00 = (size_t)y0 * Wl + x0, o01 = (size_t)y0 * Wl + x1;
-        const size_t o10 = (size_t)y1 * Wl + x0, o11 = (size_t)y1 * Wl + x1;
-        float l[CL];
-        const float* lp = p.lat + (size_t)b * CL * plane + go;
-#pragma unroll
-        for (int k = 0; k < CL; ++k) l[k] = __ldg(lp + (size_t)k * plane);
-        const bool interior = p.intra_out != nullptr && ry >= 1 && ry <= kTdTH && rx >= 1 && rx <= kTdTW;
-        float* iop = interior ? p.intra_out + (size_t)b * 64 * plane + go : nullptr;
-#pragma unroll 4
-        for (int c = 0; c < 64; ++c) {
-            const float* q = pp + (size_t)c * lplane;
-            const float up = hy * (hx * __ldg(q + o00) + lx * __ldg(q + o01)) + ly * (hx * __ldg(q + o10) + lx * __ldg(q + o11));
-            float t = 0.0f;
-#pragma unroll
-            for (int k = 0; k < CL; ++k) t = fmaf(p.w_in[k * 64 + c], l[k], t);
-            const float v = up + (t + p.b_in[c]);
-            ts[c * (kTdHH * kTdRS)] = v;
-            if (iop != nullptr) iop[(size_t)c * plane] = v;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: 3x3 output convolution from shared memory, 1x2 pixels x CO channels per thread ----------------------
-    const int tx = tid & 15, ty = tid >> 4;
-    float acc[2][CO];
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int co = 0; co < CO; ++co) acc[c][co] = 0.0f;
-    const float* tb = tile + ty * kTdRS + 2 * tx;
+template <int CL, int CO, int HALF>
+__device__ __forceinline__ void topdown_conv_half(const TopDownParams<CL, CO>& p, const float* tb0, float (&acc)[2][CO]) {
+    constexpr int CS = kTdHH * kTdRS;
+    const float* tb = tb0 + (HALF * 32) * CS;
 #pragma unroll 2
-    for (int ci = 0; ci < 64; ++ci) {
-        const float* tc = tb + ci * (kTdHH * kTdRS);
+    for (int ci = 0; ci < 32; ++ci) {
+        const float* tc = tb + ci * CS;
         float in[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -118,16 +58,108 @@ __global__ void __launch_bounds__(128, 2) fpn_topdown_kernel(const __grid_consta
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
                 for (int co = 0; co < CO; ++co) {
-                    const float wv = p.w_out[((ky * 3 + kx) * 64 + ci) * CO + co];
+                    const float wv = p.w_out[((ky * 3 + kx) * 64 + HALF * 32 + ci) * CO + co];
                     acc[0][co] = fmaf(wv, in[ky][kx], acc[0][co]);
                     acc[1][co] = fmaf(wv, in[ky][kx + 1], acc[1][co]);
                 }
     }
+}
+
+constexpr int kTdThreads = 256;
+
+template <int CL, int CO>
+__global__ void __launch_bounds__(kTdThreads, 2) fpn_topdown_kernel(const __grid_constant__ TopDownParams<CL, CO> p) {
+    extern __shared__ float tile[];  // [64][kTdHH][kTdRS]
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int tx0 = blockIdx.x * kTdTW, ty0 = blockIdx.y * kTdTH;
+    const int H = p.H, W = p.W, Hl = H / 2, Wl = W / 2;
+    const size_t plane = (size_t)H * W, lplane = (size_t)Hl * Wl;
+    constexpr int CS = kTdHH * kTdRS;  // channel stride of the tile
+
+    // ---- phase 1: the 64-channel intra tile (+ halo) -> shared memory ------------------------------------------------
+    // work item = (halo pixel, group of 16 channels); consecutive threads on consecutive pixels (coalesced planar
+    // loads, conflict-free shared-memory stores)
+    // the channel group is the OUTER, CTA-uniform loop so that the 1x1 weights stay uniform constant loads
+#pragma unroll 1
+    for (int cg = 0; cg < 4; ++cg)
+    for (int hp = tid; hp < kTdHH * kTdHW; hp += kTdThreads) {
+        const int ry = hp / kTdHW, rx = hp - ry * kTdHW;
+        const int gy = ty0 - 1 + ry, gx = tx0 - 1 + rx;
+        float* ts = tile + (cg * 16) * CS + ry * kTdRS + rx;
+        const bool inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        if (!inside) {  // zero padding of the 3x3 output convolution
+#pragma unroll
+            for (int c = 0; c < 16; ++c) ts[c * CS] = 0.0f;
+            continue;
+        }
+        const size_t go = (size_t)gy * W + gx;
+        if (p.intra_in != nullptr) {
+            const float* ip = p.intra_in + ((size_t)b * 64 + cg * 16) * plane + go;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) ts[c * CS] = __ldg(ip + (size_t)c * plane);
+            continue;
+        }
+        // bilinear x2, align_corners=True, with ATen's arithmetic (upsample_bilinear2d: source = scale * dst)
+        const float fy = p.sy * (float)gy, fx = p.sx * (float)gx;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < Hl - 1), x1 = x0 + (x0 < Wl - 1);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const float hy = 1.0f - ly, hx = 1.0f - lx;
+        const float* pp = p.prev + ((size_t)b * 64 + cg * 16) * lplane;
+        const size_t o00 = (size_t)y0 * Wl + x0, o01 = (size_t)y0 * Wl + x1;
+        const size_t o10 = (size_t)y1 * Wl + x0, o11 = (size_t)y1 * Wl + x1;
+        float l[CL];
+        const float* lp = p.lat + (size_t)b * CL * plane + go;
+#pragma unroll
+        for (int k = 0; k < CL; ++k) l[k] = __ldg(lp + (size_t)k * plane);
+        const bool interior = p.intra_out != nullptr && ry >= 1 && ry <= kTdTH && rx >= 1 && rx <= kTdTW;
+        float* iop = interior ? p.intra_out + ((size_t)b * 64 + cg * 16) * plane + go : nullptr;
+        const float* wi = p.w_in + cg * 16;
+        const float* bi = p.b_in + cg * 16;
+#pragma unroll 4
+        for (int c = 0; c < 16; ++c) {
+            const float* q = pp + (size_t)c * lplane;
+            const float up = hy * (hx * __ldg(q + o00) + lx * __ldg(q + o01)) + ly * (hx * __ldg(q + o10) + lx * __ldg(q + o11));
+            float t = 0.0f;
+#pragma unroll
+            for (int k = 0; k < CL; ++k) t = fmaf(wi[k * 64 + c], l[k], t);
+            const float v = up + (t + bi[c]);
+            ts[c * CS] = v;
+            if (iop != nullptr) iop[(size_t)c * plane] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: 3x3 output convolution from shared memory; a thread owns 1x2 pixels x CO channels for HALF of the
+    // 64 input channels (threads 0-127: channels 0-31, threads 128-255: channels 32-63), halves summed through smem ----
+    const int half = tid >> 7, t7 = tid & 127;
+    const int tx = t7 & 15, ty = t7 >> 4;
+    float acc[2][CO];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[c][co] = 0.0f;
+    // the branch is warp-uniform; inside each arm the weight offsets are compile-time constants (uniform loads)
+    if (half == 0) topdown_conv_half<CL, CO, 0>(p, tile + ty * kTdRS + 2 * tx, acc);
+    else topdown_conv_half<CL, CO, 1>(p, tile + ty * kTdRS + 2 * tx, acc);
+    __syncthreads();  // everyone is done reading the tile: reuse it for the cross-half reduction
+    float* red = tile + t7;  // [2*CO][128]
+    if (half == 1) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int co = 0; co < CO; ++co) red[(c * CO + co) * 128] = acc[c][co];
+    }
+    __syncthreads();
+    if (half == 1) return;
     const int gy = ty0 + ty, gx = tx0 + 2 * tx;
     if (gy >= H) return;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         if (gx + c >= W) break;
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[c][co] += red[(c * CO + co) * 128];
         float* fp = p.feat + ((size_t)b * plane + (size_t)gy * W + gx + c) * p.co_total + p.co_off;
 #pragma unroll
         for (int q = 0; q < CO; q += 4)
@@ -157,7 +189,7 @@ static int launch_topdown(const float* prev, const float* lat, const float* intr
     }
     dim3 grid((W + kTdTW - 1) / kTdTW, (H + kTdTH - 1) / kTdTH, B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "fpn_topdown: grid too large");
-    fpn_topdown_kernel<CL, CO><<<grid, 128, kTdSmem, s>>>(p);
+    fpn_topdown_kernel<CL, CO><<<grid, kTdThreads, kTdSmem, s>>>(p);
     count_launch();
     MVSTER_CHECK_LAUNCH("fpn_topdown launch");
     return MVSTER_OK;

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128, 3) conv5s2_kernel(const __grid_constant__
     for (int r = 0; r < 5; ++r) vy[r] = (unsigned)(2 * oy - 2 + r) < (unsigned)H;
     const bool vl = xi > 0, vr = xi + 4 < W;
     const float* xp = p.x + ((size_t)b * CIN) * plane + (size_t)(2 * oy - 2) * W + xi;
-#pragma unroll 1
+#pragma unroll kScUnroll
     for (int ci = 0; ci < CIN; ++ci) {
         const float* q = xp + (size_t)ci * plane;
         float in[5][7];

@@ -381,3 +381,52 @@ class MVS4net(nn.Module):
                                           split_itv=self.depth_interals_ratio[s], fn=filename)
             outputs[key] = stage_out
         return outputs
+
+
+class GraphedMVS4net:
+    """Inference server front end: one whole ``MVS4net.forward`` (images in, 4-stage depth out) captured as a CUDA graph.
+
+    The forward issues ~150 small launches (cuDNN layers, this library's kernels, elementwise glue); at one scene per
+    call the host-side launch cost is as large as the GPU time.  All shapes are static per (B, N, H0, W0), every kernel
+    of this library takes raw pointers and by-value weights, so the whole forward replays as a single graph launch.
+
+        g = GraphedMVS4net(model, batch=1, nviews=5, height=832, width=1152)
+        out = g(imgs, proj_matrices, depth_values)      # same nested dict as model(...); tensors are graph-owned
+    """
+
+    def __init__(self, model: MVS4net, batch: int, nviews: int, height: int, width: int, device="cuda"):
+        if model.training:
+            raise RuntimeError("GraphedMVS4net: put the model in eval mode first")
+        self.model = model
+        dev = torch.device(device)
+        self.imgs = [torch.zeros((batch, 3, height, width), device=dev) for _ in range(nviews)]
+        self.proj = {"stage%d" % (s + 1): torch.zeros((batch, nviews, 2, 4, 4), device=dev) for s in range(model.num_stage)}
+        self.depth_values = torch.ones((batch, 2), device=dev)
+        self.graph = None
+        self.out = None
+
+    def _load(self, imgs, proj_matrices, depth_values):
+        for dst, src in zip(self.imgs, imgs):
+            dst.copy_(src, non_blocking=True)
+        for k, dst in self.proj.items():
+            dst.copy_(proj_matrices[k], non_blocking=True)
+        self.depth_values.copy_(depth_values[:, [0, -1]], non_blocking=True)
+
+    def capture(self, imgs, proj_matrices, depth_values, warmup: int = 2):
+        """Warm up on real inputs (cuDNN algorithm selection, lazy module loads, weight folding), then capture."""
+        self._load(imgs, proj_matrices, depth_values)
+        with torch.no_grad():
+            for _ in range(warmup):
+                self.model(self.imgs, self.proj, self.depth_values)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self.model(self.imgs, self.proj, self.depth_values)
+        return self
+
+    def __call__(self, imgs, proj_matrices, depth_values):
+        if self.graph is None:
+            self.capture(imgs, proj_matrices, depth_values)
+        self._load(imgs, proj_matrices, depth_values)
+        self.graph.replay()
+        return self.out

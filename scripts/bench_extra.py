@@ -255,6 +255,20 @@ def bench_network(args, dev):
         torch.cuda.reset_peak_memory_stats()
         res[name + "_ms"] = timed(run, its)
         res[name + "_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
+    # the same forward as one CUDA-graph launch (fp32 and TF32-cuDNN), B = 1 and B = 2 scenes per call
+    model.stagenet, model.fuse_regnet_tail = fused_stagenet, True
+    model.__dict__.pop("extract_features", None)
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        for bb in (1, 2):
+            ims = [torch.rand((bb, 3, h0, w0), device=dev, generator=gen) for _ in range(n)]
+            pj = {k: torch.from_numpy(v).to(dev) for k, v in syn.proj_matrices_all_stages(bb, n, h0, w0).items()}
+            dvs = torch.from_numpy(syn.depth_values(bb)).to(dev)
+            gm = mv.GraphedMVS4net(model, bb, n, h0, w0, dev).capture(ims, pj, dvs)
+            ms = timed(lambda: gm(ims, pj, dvs), its)
+            res["graph_%s_b%d_ms_per_scene" % ("tf32" if tf32 else "fp32", bb)] = ms / bb
+            del gm
     # where the time goes on the B200 path (fused, fp32)
     torch.backends.cudnn.allow_tf32 = False
     model.stagenet, model.fuse_regnet_tail = fused_stagenet, True

@@ -20,6 +20,12 @@ model = model.to(dev)
 imgs = [torch.rand((b, 3, h0, w0), device=dev) for _ in range(n)]
 proj = {k: torch.from_numpy(v).to(dev) for k, v in syn.proj_matrices_all_stages(b, n, h0, w0).items()}
 dv = torch.from_numpy(syn.depth_values(b)).to(dev)
+if "--once" in sys.argv:   # for ncu: a single forward, nothing else
+    with torch.no_grad():
+        model(imgs, proj, dv)
+    torch.cuda.synchronize()
+    print("one forward done")
+    sys.exit(0)
 with torch.no_grad():
     for _ in range(3):
         model(imgs, proj, dv)
