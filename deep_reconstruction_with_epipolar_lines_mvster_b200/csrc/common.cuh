@@ -25,6 +25,20 @@ struct DeviceGuard {
     ~DeviceGuard();
 };
 
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute is per (function, device): a process
+// that drives several GPUs (nn.DataParallel, reference test_mvs4.py:393) must set it once on each of them.
+template <typename Kernel>
+static inline int ensure_dynamic_smem(Kernel kernel, int bytes, bool (&done)[64], const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return check_cuda(e, what);
+        done[dev] = true;
+    }
+    return MVSTER_OK;
+}
+
 #define MVSTER_CHECK_LAUNCH(what)                                   \
     do {                                                            \
         cudaError_t e__ = cudaGetLastError();                       \

@@ -791,12 +791,10 @@ static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
     constexpr int TB = C * (int)sizeof(T);
     const int smem = MVSTER_MAX_SRC_VIEWS * 48 +
                      (TMA ? 2 * TmaGeom<C>::BW * (TILE_H + TmaGeom<C>::BH_EXTRA) * TB + 1024 + TmaGeom<C>::CTL_BYTES : 0);
-    static bool attr_set = false;  // per-function attribute, idempotent
-    if (smem > 48 * 1024 && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(epi_fwd_kernel<C, CPG, D, TMA, T>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return check_cuda(e, "epi_fwd: cudaFuncSetAttribute");
-        attr_set = true;
+    static bool attr_done[64] = {};
+    if (smem > 48 * 1024) {
+        const int st = ensure_dynamic_smem(epi_fwd_kernel<C, CPG, D, TMA, T>, smem, attr_done, "epi_fwd: cudaFuncSetAttribute");
+        if (st != MVSTER_OK) return st;
     }
     dim3 grid((p.W + S::TILE_W - 1) / S::TILE_W, (p.H + TILE_H - 1) / TILE_H, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
@@ -826,13 +824,9 @@ static bool make_line_maps(EpiFwdParams& p, int Nsrc, int B, int Hs, int Ws) {
 template <int CPG, int D>
 static int launch_line(const EpiFwdParams& p, cudaStream_t stream) {
     using Gm = LineGeom;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(epi_fwd_line_kernel<CPG, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Gm::SMEM);
-        if (e != cudaSuccess) return check_cuda(e, "epi_fwd(line): cudaFuncSetAttribute");
-        attr_set = true;
-    }
+    static bool attr_done[64] = {};
+    const int st = ensure_dynamic_smem(epi_fwd_line_kernel<CPG, D>, Gm::SMEM, attr_done, "epi_fwd(line): cudaFuncSetAttribute");
+    if (st != MVSTER_OK) return st;
     dim3 grid((p.W + Gm::TILE_W - 1) / Gm::TILE_W, (p.H + Gm::TILE_H - 1) / Gm::TILE_H, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
     epi_fwd_line_kernel<CPG, D><<<grid, Gm::WARPS * 32, Gm::SMEM, stream>>>(p);

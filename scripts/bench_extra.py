@@ -8,6 +8,7 @@
   train    config 4 (single GPU part): K1 forward+backward at 512x640, B=2, N=5 through EpipolarAggregate
   filter   config 5: 49 views 512x640, 9 sources each, fused geometric/photometric filter
   ref_gpu  plain-PyTorch (eager, stock ATen kernels) restatement of the same op on the same GPU, as context
+  config0  BASELINE configs[0]: whole MVS4net forward 512x640 N=5 on the host CPU (reference op sequence) vs the B200 path
   network  whole MVS4net.forward (FPN4 + reg2d via cuDNN, fused stagenet / regulariser tail) vs the eager op sequence
 """
 from __future__ import annotations
@@ -291,15 +292,77 @@ def bench_network(args, dev):
     print(json.dumps(res))
 
 
+def bench_config0(args, dev):
+    """BASELINE.json configs[0]: MVS4Net 4-stage forward, DTU-train shape B=1 N=5 512x640, ndepths 8-8-4-4, fp32 -
+    the reference's op sequence on the host CPU cores (all threads) next to the B200 path on the same inputs."""
+    h0, w0, n, b = 512, 640, 5, 1
+    model = mv.MVS4net(**NET_CFG).eval()
+    model.load_state_dict(syn.fill_state_dict(model.state_dict(), seed=7))
+    gen = torch.Generator().manual_seed(0)
+    imgs = [torch.rand((b, 3, h0, w0), generator=gen) for _ in range(n)]
+    proj = {k: torch.from_numpy(v) for k, v in syn.proj_matrices_all_stages(b, n, h0, w0).items()}
+    dv = torch.from_numpy(syn.depth_values(b))
+    # CPU: per-view NCHW FPN, eager warp / correlation / attention, reg2d, torch tail - the reference's op sequence
+    # (the schedule comes from the oracle: this package has no CPU path)
+    from oracle import mvster_oracle as O
+    eager = _EagerStagenet()
+
+    def cpu_forward():
+        feats = [model.feature(i) for i in imgs]
+        outs, st = {}, None
+        for si in range(4):
+            key = "stage%d" % (si + 1)
+            fs = [f[key] for f in feats]
+            hh, ww = fs[0].shape[2:]
+            d = NET_CFG["stage_splits"][si]
+            if si == 0:
+                hypo = torch.from_numpy(O.init_inverse_range_np(dv.numpy(), d, hh, ww))
+            else:
+                hypo = torch.from_numpy(O.schedule_inverse_range_np(st["inverse_min_depth"].numpy(),
+                                                                    st["inverse_max_depth"].numpy(), d, hh, ww))
+            st = eager(fs, proj[key], hypo, model.reg[si], si, group_cor_dim=NET_CFG["group_cor_dim"][si],
+                       split_itv=NET_CFG["depth_interals_ratio"][si])
+            outs[key] = st
+        return outs
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        cpu_forward()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            out_cpu = cpu_forward()
+        cpu_s = (time.perf_counter() - t0) / reps
+    model = model.to(dev)
+    torch.backends.cudnn.allow_tf32 = False
+    dimgs = [i.to(dev) for i in imgs]
+    dproj = {k: v.to(dev) for k, v in proj.items()}
+    ddv = dv.to(dev)
+
+    def run():
+        with torch.no_grad():
+            return model(dimgs, dproj, ddv)
+
+    ms = timed(run, max(5, args.iters // 2))
+    out = run()
+    a, r = out["stage1"]["attn_weight"].cpu(), out_cpu["stage1"]["attn_weight"]
+    agree = (out["stage4"]["depth"].cpu() - out_cpu["stage4"]["depth"]).abs() < 1e-3 * 2.5
+    print(json.dumps({"bench": "config0_mvs4net_forward_512x640_n5_fp32", "cpu_reference_like_s": cpu_s,
+                      "cpu_threads": torch.get_num_threads(), "cpu_depth_maps_per_s": 1.0 / cpu_s, "b200_ms": ms,
+                      "b200_depth_maps_per_s": 1e3 / ms, "speedup": cpu_s * 1e3 / ms,
+                      "stage1_attn_max_abs_diff": float((a - r).abs().max()),
+                      "stage4_depth_agree_frac": float(agree.float().mean())}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network")
+    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network,config0")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--cpu-filter-pairs", type=int, default=20)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     fns = {"stages": bench_stages, "binpick": bench_binpick, "train": bench_train, "filter": bench_filter,
-           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network}
+           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network, "config0": bench_config0}
     for name in args.which.split(","):
         fns[name](args, dev)
 

@@ -408,3 +408,20 @@ def test_k1_reference_option_variants(golden, name, group_cor, attn_fuse_d):
     with torch.no_grad():
         net(feats, proj, hypo, regnet, 1, group_cor=group_cor, group_cor_dim=groups, split_itv=1.0)
     assert torch.equal(seen["x"], got)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process (nn.DataParallel pattern)")
+def test_second_device_in_the_same_process(golden):
+    """One host process driving two GPUs (reference test_mvs4.py:393, nn.DataParallel): the device comes from the
+    pointers, and per-function attributes (dynamic shared memory of the TMA kernels) are set on every device."""
+    for name in ("k1_stage4", "k1_stage2"):
+        g = golden(name)
+        outs = []
+        for dev in ("cuda:0", "cuda:1"):
+            feats = [torch.from_numpy(g["ref"]).to(dev)] + \
+                    [torch.from_numpy(g["srcs"][:, v]).to(dev) for v in range(g["srcs"].shape[1])]
+            outs.append(mv.epipolar_aggregate(feats, torch.from_numpy(g["proj"]).to(dev),
+                                              torch.from_numpy(g["hypo"]).to(dev), int(g["groups"]),
+                                              float(g["attn_temp"])).cpu())
+        assert torch.equal(outs[0], outs[1])
+        assert np.abs(outs[1].numpy() - g["volume"]).max() < 1e-4
