@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue the 16 launches of a step eagerly instead of replaying them as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin each rank (N > 1) to the CPUs local to its GPU before allocating pinned buffers")
     ap.add_argument("--cpu-scenes", type=int, default=10, help="timed scenes of the CPU baseline sample")
     return ap.parse_args()
 
@@ -272,6 +274,9 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from deep_reconstruction_with_epipolar_lines_mvster_b200.sharding import bind_to_gpu_numa_node
+    # only with several ranks per box: at N=1 there is no contention, and the CPU baseline wants every host core
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if (world > 1 and not args.no_numa_bind) else None
     if world > 1:
         dist.init_process_group("nccl", init_method="env://", device_id=dev)
 
@@ -370,7 +375,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "fp32" else "bf16 features, f32 accumulate", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world), host_affinity=(
+                "each rank bound to its GPU's local NUMA CPUs (%d cpus on rank 0)" % len(numa_cpus)) if numa_cpus
+                else "unbound (single rank, topology not exposed, or --no-numa-bind)"),
             "clocks": sampler.summary(),
             "e2e": {"value": args.scenes * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": plan.h2d_bytes(), "d2h_bytes_per_step": plan.d2h_bytes(),

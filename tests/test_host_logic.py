@@ -79,6 +79,13 @@ def test_sharding_round_robin():
         mv.shard_round_robin(8, 2, 2)
 
 
+def test_numa_cpu_list_parsing_and_graceful_absence():
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    if not torch.cuda.is_available():   # no GPU: the topology lookup must return None, not raise
+        assert sharding.gpu_local_cpus(0) is None and sharding.bind_to_gpu_numa_node(0) is None
+
+
 def test_synthetic_rig_layout():
     p = syn.proj_matrices(2, 5, 512, 640, 0)
     assert p.shape == (2, 5, 2, 4, 4) and p.dtype == np.float32
