@@ -338,3 +338,47 @@ extern "C" int mvster_geo_filter(const float* depths, const float* confs, const 
     if (le != cudaSuccess) return check_cuda(le, "geo_filter launch");
     return MVSTER_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// depth2pts (reference test_mvs4.py:206-218, pixel grid :220-229): back-projection of a fused depth map to world points
+//     uv = K^-1 [x+0.5, y+0.5, 1]^T ;  X_cam = uv * depth ;  X_world = R^-1 (X_cam - t)          (float64 throughout)
+// One thread per pixel, 4 bytes in, 24 bytes out, fully coalesced; stays on the GPU between the filter and the
+// point-cloud writer instead of the reference's NumPy temporaries of shape [3, H*W] float64.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace mvster {
+struct Depth2PtsCam {
+    double kinv[9], rinv[9], t[3];
+};
+__global__ void __launch_bounds__(256) depth2pts_kernel(const float* __restrict__ depth, double* __restrict__ xyz,
+                                                        const __grid_constant__ Depth2PtsCam c, int H, int W) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)H * W) return;
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    const double px = (double)x + 0.5, py = (double)y + 0.5;  // np.linspace(0.5, W - 0.5, W)
+    const double d = (double)depth[i];
+    const double cx = (c.kinv[0] * px + c.kinv[1] * py + c.kinv[2]) * d - c.t[0];
+    const double cy = (c.kinv[3] * px + c.kinv[4] * py + c.kinv[5]) * d - c.t[1];
+    const double cz = (c.kinv[6] * px + c.kinv[7] * py + c.kinv[8]) * d - c.t[2];
+    xyz[3 * i + 0] = c.rinv[0] * cx + c.rinv[1] * cy + c.rinv[2] * cz;
+    xyz[3 * i + 1] = c.rinv[3] * cx + c.rinv[4] * cy + c.rinv[5] * cz;
+    xyz[3 * i + 2] = c.rinv[6] * cx + c.rinv[7] * cy + c.rinv[8] * cz;
+}
+}  // namespace mvster
+
+extern "C" int mvster_depth2pts(const float* depth, const double* K, const double* E, double* xyz, int H, int W,
+                                void* stream) {
+    if (!depth || !K || !E || !xyz) return fail(MVSTER_ERR_BAD_ARG, "depth2pts: null pointer");
+    if (H <= 0 || W <= 0) return fail(MVSTER_ERR_BAD_ARG, "depth2pts: non-positive dimension");
+    DeviceGuard guard(xyz);
+    if (guard.status != MVSTER_OK) return guard.status;
+    Depth2PtsCam c;
+    inv3(K, c.kinv);                                   // np.linalg.inv(cam_intrinsic), :209
+    const double R[9] = {E[0], E[1], E[2], E[4], E[5], E[6], E[8], E[9], E[10]};
+    inv3(R, c.rinv);                                   // np.linalg.inv(R), :214
+    c.t[0] = E[3]; c.t[1] = E[7]; c.t[2] = E[11];
+    const size_t n = (size_t)H * W;
+    depth2pts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(depth, xyz, c, H, W);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("depth2pts launch");
+    return MVSTER_OK;
+}

@@ -376,6 +376,18 @@ def _dbl(a, n) -> "ctypes.Array":
     return arr
 
 
+def depth2pts(depth: torch.Tensor, k, e) -> torch.Tensor:
+    """World points [H*W,3] float64 of a depth map (reference depth2pts_np, test_mvs4.py:206-218)."""
+    dz = _f32c(depth, "depth")
+    h, w = dz.shape
+    xyz = torch.empty((h * w, 3), device=dz.device, dtype=torch.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    kk, ee = _dbl(k, 9), _dbl(e, 16)
+    _lib.check(_lib.load().mvster_depth2pts(_ptr(dz), kk.ctypes.data_as(dp), ee.ctypes.data_as(dp), _ptr(xyz), h, w,
+                                            _stream(dz)))
+    return xyz
+
+
 def geo_check_pair(depth_ref: torch.Tensor, k_ref, e_ref, depth_src: torch.Tensor, k_src, e_src,
                    condmask_pixel: float, condmask_depth: float):
     dr, ds = _f32c(depth_ref, "depth_ref"), _f32c(depth_src, "depth_src")

@@ -203,6 +203,12 @@ int mvster_geo_filter(const float* depths, const float* confs, const double* K, 
                       uint8_t* photo, uint8_t* geo, uint8_t* final_mask, float* depth_avg, int32_t* geo_sum, int H,
                       int W, void* stream);
 
+/* ---- depth2pts: fused depth map -> world points, reference test_mvs4.py:206-229 ---------
+ *   depth dev [H, W] fp32;  K HOST [9], E HOST [16] float64 row-major;  xyz dev [H*W, 3] float64 (row-major pixel order)
+ *   X_world = R^-1 (K^-1 [x+0.5, y+0.5, 1]^T * depth - t), all in float64 as the reference's NumPy arithmetic.
+ */
+int mvster_depth2pts(const float* depth, const double* K, const double* E, double* xyz, int H, int W, void* stream);
+
 /* ---- layout helper: NCHW fp32 -> NHWC fp32/bf16 (the FPN emits NCHW, models/mvs4net_utils.py:504-507) ----- */
 int mvster_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_dtype, void* stream);
 

@@ -448,6 +448,17 @@ def check_geometric_consistency_np(depth_ref, k_ref, e_ref, depth_src, k_src, e_
     return mask, d_rep, x_src, y_src
 
 
+def depth2pts_np(depth_map: np.ndarray, cam_intrinsic: np.ndarray, cam_extrinsic: np.ndarray) -> np.ndarray:
+    """World points [H*W,3] float64 of a depth map: pixel-centre grid (x+0.5, y+0.5, 1), ``K^-1``, times depth, then
+    ``R^-1 (X - t)`` (test_mvs4.py:206-229)."""
+    h, w = depth_map.shape
+    xs, ys = np.meshgrid(np.linspace(0.5, w - 0.5, w), np.linspace(0.5, h - 0.5, h))
+    grid = np.stack([xs.reshape(-1), ys.reshape(-1), np.ones(h * w)], 0)
+    cam = (np.linalg.inv(cam_intrinsic) @ grid) * depth_map.reshape(1, -1)
+    r, t = cam_extrinsic[:3, :3], cam_extrinsic[:3, 3:4]
+    return (np.linalg.inv(r) @ (cam - t)).T
+
+
 def filter_fuse_np(depths: np.ndarray, confs: np.ndarray, ks: np.ndarray, es: np.ndarray, pairs: np.ndarray,
                    condmask_pixel: float, condmask_depth: float, photomask: float, geomask: int,
                    use_cv2: bool = False):

@@ -9,6 +9,7 @@
   filter   config 5: 49 views 512x640, 9 sources each, fused geometric/photometric filter
   ref_gpu  plain-PyTorch (eager, stock ATen kernels) restatement of the same op on the same GPU, as context
   config0  BASELINE configs[0]: whole MVS4net forward 512x640 N=5 on the host CPU (reference op sequence) vs the B200 path
+  scene    49-view scene end to end on the GPU: depth maps -> filter -> point cloud
   network  whole MVS4net.forward (FPN4 + reg2d via cuDNN, fused stagenet / regulariser tail) vs the eager op sequence
 """
 from __future__ import annotations
@@ -354,15 +355,75 @@ def bench_config0(args, dev):
                       "stage4_depth_agree_frac": float(agree.float().mean())}))
 
 
+def bench_scene(args, dev):
+    """Whole-scene reconstruction, GPU-resident (BASELINE configs[4] extended to the full test_mvs4.py pipeline):
+    49 views 512x640 -> 49 depth + confidence maps (MVS4net, N=5 views each, one CUDA-graph replay per reference view)
+    -> photometric/geometric filter over 49x9 pairs -> averaged depth -> world points of the kept pixels.  Nothing
+    leaves the GPU between the stages (the reference writes and re-reads 98 .pfm files in between)."""
+    h0, w0, v, nv, s = 512, 640, 49, 5, 9
+    model = mv.MVS4net(**NET_CFG).eval()
+    model.load_state_dict(syn.fill_state_dict(model.state_dict(), seed=7))
+    model = model.to(dev)
+    torch.backends.cudnn.allow_tf32 = False
+    gen = torch.Generator(device=dev).manual_seed(0)
+    images = torch.rand((v, 3, h0, w0), device=dev, generator=gen)
+    k = syn.intrinsics(h0, w0, 3)
+    es = np.stack([syn.grid_extrinsics(i, 7, 0.04) for i in range(v)])
+    ks = np.stack([k] * v)
+    nbrs = syn.pair_list(v, s)                                     # [V, 9] source views, nearest first
+    pairs = np.concatenate([np.arange(v)[:, None], nbrs], 1).astype(np.int32)
+    dv = torch.from_numpy(syn.depth_values(1)).to(dev)
+
+    def projections(ref):
+        views = [ref] + [int(x) for x in nbrs[ref][:nv - 1]]
+        out = {}
+        for st in range(4):
+            p = np.zeros((1, nv, 2, 4, 4), np.float32)
+            kk = syn.intrinsics(h0, w0, st)
+            for j, vi in enumerate(views):
+                p[0, j, 0] = es[vi]
+                p[0, j, 1, :3, :3] = kk
+            out["stage%d" % (st + 1)] = torch.from_numpy(p).to(dev)
+        return views, out
+
+    pre = [projections(r) for r in range(v)]
+    gm = mv.GraphedMVS4net(model, 1, nv, h0, w0, dev)
+    depths = torch.empty((v, h0, w0), device=dev)
+    confs = torch.empty((v, h0, w0), device=dev)
+    cfg = mv.FilterConfig(photomask=0.0)   # random-init weights: keep every pixel the geometry accepts
+
+    def run():
+        for r in range(v):
+            views, proj = pre[r]
+            out = gm([images[i:i + 1] for i in views], proj, dv)["stage4"]
+            depths[r].copy_(out["depth"][0])
+            confs[r].copy_(out["photometric_confidence"][0])
+        return mv.fuse_scene(depths, confs, ks, es, pairs, images=images.permute(0, 2, 3, 1), config=cfg)
+
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        verts, cols, info = run()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    print(json.dumps({"bench": "scene_49views_512x640_depth_filter_points", "seconds_per_scene": dt,
+                      "depth_maps_per_s": v / dt, "points_kept": int(verts.shape[0]),
+                      "final_mask_mean": float(info["final"].float().mean()),
+                      "note": "random-init network: depth maps are not geometrically consistent, so few points survive; "
+                              "the timing does not depend on it"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network,config0")
+    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network,config0,scene")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--cpu-filter-pairs", type=int, default=20)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     fns = {"stages": bench_stages, "binpick": bench_binpick, "train": bench_train, "filter": bench_filter,
-           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network, "config0": bench_config0}
+           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network, "config0": bench_config0, "scene": bench_scene}
     for name in args.which.split(","):
         fns[name](args, dev)
 

@@ -425,3 +425,35 @@ def test_second_device_in_the_same_process(golden):
                                               float(g["attn_temp"])).cpu())
         assert torch.equal(outs[0], outs[1])
         assert np.abs(outs[1].numpy() - g["volume"]).max() < 1e-4
+
+
+# --------------------------------------------------------------------------------------------------------------
+# fusion tail: depth2pts + masked point selection
+# --------------------------------------------------------------------------------------------------------------
+def test_depth2pts_matches_reference(golden):
+    g, f = golden("fusion"), golden("filter")
+    for i in range(len(f["pairs"])):
+        r = int(f["pairs"][i, 0])
+        d32 = np.nan_to_num(f["depth_avg"][i]).astype(np.float32)   # the reference's average is float64; ours is fp32
+        pts = mv.depth2pts(_cuda(d32), f["ks"][r], f["es"][r]).cpu().numpy()
+        ref = g["points"][i]
+        ok = np.isfinite(ref).all(1)
+        assert pts.shape == ref.shape and pts.dtype == np.float64
+        assert np.abs(pts - O.depth2pts_np(d32.astype(np.float64), f["ks"][r], f["es"][r])).max() < 1e-9
+        assert np.abs(pts[ok] - ref[ok]).max() < 2e-4                # fp32 rounding of a ~700 mm depth
+    # numpy in -> numpy out, like the reference's depth2pts_np
+    out = mv.depth2pts(np.nan_to_num(f["depth_avg"][0]), f["ks"][0], f["es"][0])
+    assert isinstance(out, np.ndarray) and out.shape == (f["depth_avg"][0].size, 3)
+
+
+def test_fuse_scene_matches_reference_point_cloud(golden):
+    """filter -> averaged depth -> world points -> masked selection, all on the GPU, against the reference's vertices
+    and colours (same order: reference views in pair-file order, pixels row-major)."""
+    g, f = golden("fusion"), golden("filter")
+    cfg = mv.FilterConfig(float(f["condmask_pixel"]), float(f["condmask_depth"]), float(f["photomask"]), int(f["geomask"]))
+    verts, cols, info = mv.fuse_scene(f["depths"], f["conf"], f["ks"], f["es"], f["pairs"], images=g["images"], config=cfg)
+    assert (info["final"].cpu().numpy().astype(bool) == f["final"]).mean() >= 0.9999
+    if np.array_equal(info["final"].cpu().numpy().astype(bool), f["final"]):
+        assert verts.shape == g["vertices"].shape
+        assert np.abs(verts.cpu().numpy() - g["vertices"]).max() < 2e-3       # averaged depth is fp32: ~1e-4 mm
+        assert np.array_equal(cols.cpu().numpy(), g["colors"])
