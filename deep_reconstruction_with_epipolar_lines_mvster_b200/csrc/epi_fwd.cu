@@ -151,6 +151,24 @@ __device__ __forceinline__ void bbox_update(int* slot, float lox, float loy, flo
     }
 #endif
 }
+// 8 channels of one texel from the staged box as 4 packed fp32 pairs.  `a` is the (swizzled) address of the chunk's
+// first 16 bytes.  fp32: 32 bytes = two LDS.128, the second half sits at a ^ 16 in both swizzle modes;
+// bf16: 16 bytes = one LDS.128, widened to fp32 (exact).
+template <typename T>
+__device__ __forceinline__ void lds_chunk8(uint32_t a, P8& t) {
+    if constexpr (sizeof(T) == 4) {
+        lds_pairs(a, t.q[0], t.q[1]);
+        lds_pairs(a ^ 16u, t.q[2], t.q[3]);
+    } else {
+        uint32_t x, y, z, w;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a));
+        t.q[0] = pack2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+        t.q[1] = pack2(__uint_as_float(y << 16), __uint_as_float(y & 0xffff0000u));
+        t.q[2] = pack2(__uint_as_float(z << 16), __uint_as_float(z & 0xffff0000u));
+        t.q[3] = pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
@@ -161,7 +179,8 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
     constexpr int G = C / CPG;
     constexpr int WX = S::WX, TILE_H = S::TILE_H;  // CTA tile: 32 x 8 pixels
     constexpr int TB = C * (int)sizeof(T); // texel bytes
-    static_assert(!TMA || (sizeof(T) == 4 && (C == 8 || C == 16) && LC == 1 && S::TILE_W == 32), "TMA variant: fp32, C in {8,16}");
+    static_assert(!TMA || (TB >= 16 && TB <= 64 && LC == 1 && S::TILE_W == 32), "TMA variant: 16/32/64-byte texels");
+    constexpr uint32_t CHB = 8u * (uint32_t)sizeof(T);  // bytes of one 8-channel chunk
 
     extern __shared__ unsigned char smem_raw[];
     // TMA variant: [buf0 | buf1] 1024-aligned, then 2 mbarriers + 3 bbox slots; both variants: homographies at the end
@@ -318,14 +337,10 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
                         const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + xo;
                         const uint32_t mA = (xo >> 3) & SWZ, mB = ((xo + TB) >> 3) & SWZ;
                         const uint32_t aL = base ^ mA, aR = (base + TB) ^ mB;
-                        lds_pairs(aL, t00.q[0], t00.q[1]);
-                        lds_pairs(aL ^ 16u, t00.q[2], t00.q[3]);
-                        lds_pairs(aR, t01.q[0], t01.q[1]);
-                        lds_pairs(aR ^ 16u, t01.q[2], t01.q[3]);
-                        lds_pairs(aL + ROW_BYTES, t10.q[0], t10.q[1]);
-                        lds_pairs((aL ^ 16u) + ROW_BYTES, t10.q[2], t10.q[3]);
-                        lds_pairs(aR + ROW_BYTES, t11.q[0], t11.q[1]);
-                        lds_pairs((aR ^ 16u) + ROW_BYTES, t11.q[2], t11.q[3]);
+                        lds_chunk8<T>(aL, t00);
+                        lds_chunk8<T>(aR, t01);
+                        lds_chunk8<T>(aL + ROW_BYTES, t10);
+                        lds_chunk8<T>(aR + ROW_BYTES, t11);
                     }
                     prx = rx; pry = ry;
                     const float gx = 1.0f - fx, gy = 1.0f - fy;
@@ -352,16 +367,12 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
                 const float w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
 #pragma unroll
                 for (int k = 0; k < NCHUNK; ++k) {
-                    const uint32_t aL = (base + 32u * k) ^ mA, aR = (base + TB + 32u * k) ^ mB;
+                    const uint32_t aL = (base + CHB * k) ^ mA, aR = (base + TB + CHB * k) ^ mB;
                     P8 t00, t01, t10, t11;
-                    lds_pairs(aL, t00.q[0], t00.q[1]);
-                    lds_pairs(aL ^ 16u, t00.q[2], t00.q[3]);
-                    lds_pairs(aR, t01.q[0], t01.q[1]);
-                    lds_pairs(aR ^ 16u, t01.q[2], t01.q[3]);
-                    lds_pairs(aL + ROW_BYTES, t10.q[0], t10.q[1]);
-                    lds_pairs((aL ^ 16u) + ROW_BYTES, t10.q[2], t10.q[3]);
-                    lds_pairs(aR + ROW_BYTES, t11.q[0], t11.q[1]);
-                    lds_pairs((aR ^ 16u) + ROW_BYTES, t11.q[2], t11.q[3]);
+                    lds_chunk8<T>(aL, t00);
+                    lds_chunk8<T>(aR, t01);
+                    lds_chunk8<T>(aL + ROW_BYTES, t10);
+                    lds_chunk8<T>(aR + ROW_BYTES, t11);
                     float cg[8 / CPG];
                     blend_correlate<CPG>(t00, t01, t10, t11, w00, w01, w10, w11, rf + k * 4, cg);
 #pragma unroll
@@ -764,19 +775,23 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int C, int CPG, int D>
+template <int C, int CPG, int D, typename T>
 static bool make_maps(EpiFwdParams& p, int Nsrc, int B, int Hs, int Ws) {
+    constexpr int ES = (int)sizeof(T), TBY = C * ES;
     using S = Split<C, CPG, D>;
     constexpr int TILE_H = S::TILE_H;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Ws * C * 4, (cuuint64_t)Hs * Ws * C * 4};
+    const cuuint64_t strides[3] = {(cuuint64_t)TBY, (cuuint64_t)Ws * TBY, (cuuint64_t)Hs * Ws * TBY};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TmaGeom<C>::BW, (cuuint32_t)(TILE_H + TmaGeom<C>::BH_EXTRA), 1};
-    const CUtensorMapSwizzle swz = (C == 8) ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+    // the swizzle span equals the texel size: 8 neighbouring texels land in 8 different 16-byte bank groups
+    const CUtensorMapSwizzle swz = TBY == 16 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                   : (TBY == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+    const CUtensorMapDataType dt = ES == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     for (int v = 0; v < Nsrc; ++v) {
-        CUresult r = enc(&p.tmap[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p.src[v]), dims, strides, box,
+        CUresult r = enc(&p.tmap[v], dt, 4, const_cast<void*>(p.src[v]), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return false;
@@ -837,10 +852,16 @@ static int launch_line(const EpiFwdParams& p, cudaStream_t stream) {
 
 template <int C, int CPG, int D>
 static int dispatch_variant(EpiFwdParams& p, int dtype, bool allow_tma, cudaStream_t s) {
-    if (dtype == MVSTER_BF16) return launch_direct<C, CPG, D, __nv_bfloat16>(p, s);
+    if (dtype == MVSTER_BF16) {
+        if constexpr (C <= 16) {  // 16/32-byte bf16 texels (fine stages): the same TMA-staged swizzled-box gather
+            if (allow_tma && make_maps<C, CPG, D, __nv_bfloat16>(p, p.Nsrc, p.B, p.Hs, p.Ws))
+                return launch_fwd<C, CPG, D, true, __nv_bfloat16>(p, s);
+        }
+        return launch_direct<C, CPG, D, __nv_bfloat16>(p, s);
+    }
     if constexpr (C == 8 || C == 16) {
         // fine stages (32/64-byte fp32 texels): TMA-staged shared-memory gather when the tensor maps can be built
-        if (allow_tma && make_maps<C, CPG, D>(p, p.Nsrc, p.B, p.Hs, p.Ws)) return launch_fwd<C, CPG, D, true, float>(p, s);
+        if (allow_tma && make_maps<C, CPG, D, float>(p, p.Nsrc, p.B, p.Hs, p.Ws)) return launch_fwd<C, CPG, D, true, float>(p, s);
     }
     if constexpr (C == 32 && CPG <= 4) {
         // whole-line texels: conflict-free rotated shared-memory gather (see epi_fwd_line_kernel)

@@ -200,3 +200,19 @@ def test_cascade_free_running_vs_cpu_port():
     assert close.float().mean().item() > 0.995, close.float().mean().item()
     ok = close & torch.isfinite(want_c) & (want_c.abs() < 1e3)
     assert torch.allclose(conf[ok], want_c[ok], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+def test_k1_bf16_tma_path_full_size_equals_direct_path(stage, monkeypatch):
+    """bf16 features at the fine stages (16/32-byte texels) go through the TMA-staged swizzled box as well; the
+    direct-gather kernel (MVSTER_NO_TMA=1) computes the same sums in the same order per pixel."""
+    feats, proj, hypo, g, d, h, w = _stage(stage, batch=1, seed=11)
+    dfe = [f.to(DEV).bfloat16() for f in feats]
+    dproj, dhyp = torch.from_numpy(proj).to(DEV), torch.from_numpy(hypo).to(DEV)
+    vol = mv.epipolar_aggregate(dfe, dproj, dhyp, g, 2.0)
+    monkeypatch.setenv("MVSTER_NO_TMA", "1")
+    vol_d = mv.epipolar_aggregate(dfe, dproj, dhyp, g, 2.0)
+    assert (vol - vol_d).abs().max().item() < 5e-6
+    ref64, _, _ = O.epipolar_aggregate_np(feats[0].bfloat16().float().numpy(), [f.bfloat16().float().numpy() for f in feats[1:]],
+                                          proj, hypo, g, 2.0, window=(0, 16, 0, 24))
+    assert np.abs(vol[:, :, :, :16, :24].cpu().numpy() - ref64).max() < 1e-4

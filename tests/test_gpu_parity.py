@@ -77,7 +77,7 @@ def test_k1_backward_is_reproducible_within_atomic_tolerance(golden):
         assert (a - b).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("name", ["k1_stage2", "k1_stage4"])
+@pytest.mark.parametrize("name", ["k1_stage1", "k1_stage2", "k1_stage3", "k1_stage4", "k1_oob"])
 def test_k1_bf16_features(golden, name):
     g = golden(name)
     feats = _features(g)
