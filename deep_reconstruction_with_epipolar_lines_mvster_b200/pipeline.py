@@ -77,14 +77,17 @@ class CascadePlan:
         return sum(f.numel() * f.element_size() for fs in self.features for f in fs)
 
     # ---- the hot path ------------------------------------------------------------------------------------------------
-    def run(self, time_stage: Optional[int] = None):
+    def run(self, time_stage: Optional[int] = None, stage_ready: Optional[Sequence] = None):
         """Issue all stages on the current stream.  If ``time_stage`` is given and ``self.stage_events`` holds a
-        (start, end) event pair, the pair brackets that stage's K1 launch."""
+        (start, end) event pair, the pair brackets that stage's K1 launch.  ``stage_ready[s]`` (optional CUDA events)
+        are waited on before stage ``s`` starts (its inputs arrive on another stream)."""
         lib, check, P = self.lib, _lib.check, ops._ptr
         st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         B, N = self.B, self.N
         for s in range(self.nstage):
             (h, w), c, g, d = self.shapes[s], self.channels[s], self.groups[s], self.ndepths[s]
+            if stage_ready is not None:
+                torch.cuda.current_stream(self.device).wait_event(stage_ready[s])
             if s == 0:
                 check(lib.mvster_init_inverse_range(P(self.depth_values), 2, P(self.hypo[0]), B, d, h, w, st))
             else:
@@ -144,15 +147,25 @@ class CascadePlan:
 
     def run_from_host(self):
         """Copy this step's inputs from pinned host memory, run the cascade, copy depth + confidence back; returns
-        after the results are on the host (the call a user with host-side data makes)."""
-        for hf, df in zip(self.h_features, self.features):
-            for a, b in zip(hf, df):
-                b.copy_(a, non_blocking=True)
-        for a, b in zip(self.h_proj, self.proj):
-            b.copy_(a, non_blocking=True)
-        self.depth_values.copy_(self.h_depth_values, non_blocking=True)
-        depth, conf = self.run()
+        after the results are on the host (the call a user with host-side data makes).
+
+        The copies of stage k+1's features are issued on a side stream while stage k computes (the link, not the GPU,
+        is the bottleneck: 2.4 GB in per step against ~2 ms of kernels), so only the last stage's kernels are exposed."""
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage_ready = [torch.cuda.Event() for _ in range(self.nstage)]
+        cs = self._copy_stream
+        cs.wait_stream(cur)  # the previous step's kernels are done reading the device buffers
+        with torch.cuda.stream(cs):
+            self.depth_values.copy_(self.h_depth_values, non_blocking=True)
+            for s in range(self.nstage):
+                self.proj[s].copy_(self.h_proj[s], non_blocking=True)
+                for a, b in zip(self.h_features[s], self.features[s]):
+                    b.copy_(a, non_blocking=True)
+                self._stage_ready[s].record(cs)
+        depth, conf = self.run(stage_ready=self._stage_ready)
         self.h_depth.copy_(depth, non_blocking=True)
         self.h_conf.copy_(conf, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        cur.synchronize()
         return self.h_depth, self.h_conf
