@@ -22,7 +22,7 @@ namespace mvster {
 constexpr int kTdTW = 32, kTdTH = 8;                 // output tile
 constexpr int kTdHW = kTdTW + 2, kTdHH = kTdTH + 2;  // tile + halo
 constexpr int kTdRS = 36;                            // shared-memory row stride in floats (even: 8-byte aligned pairs)
-constexpr int kTdSmem = 64 * kTdHH * kTdRS * 4;      // 92160 bytes
+constexpr int kTdSmem = (64 * kTdHH * kTdRS + 16 * 64 + 64) * 4;  // tile (92160 bytes) + lateral weights and bias
 
 template <int CL, int CO>
 struct TopDownParams {
@@ -78,26 +78,34 @@ __global__ void __launch_bounds__(kTdThreads, 2) fpn_topdown_kernel(const __grid
     constexpr int CS = kTdHH * kTdRS;  // channel stride of the tile
 
     // ---- phase 1: the 64-channel intra tile (+ halo) -> shared memory ------------------------------------------------
-    // work item = (halo pixel, group of 16 channels); consecutive threads on consecutive pixels (coalesced planar
-    // loads, conflict-free shared-memory stores)
-    // the channel group is the OUTER, CTA-uniform loop so that the 1x1 weights stay uniform constant loads
+#if !defined(MVSTER_TD_SKIP) || MVSTER_TD_SKIP != 1
+    // work item = (32 consecutive halo pixels, 8 channels): 11 pixel chunks x 8 channel groups = 88 warp-items, exactly
+    // 11 per warp (a pixel-major split leaves two thirds of the CTA idle at the barrier in its second round).  The
+    // channel group is warp-uniform but not CTA-uniform, so the lateral 1x1 weights are read as shared-memory
+    // broadcasts instead of uniform constant loads.
+    float* w_s = tile + 64 * CS;         // [CL][64] lateral weights, then [64] bias
+    for (int i = tid; i < CL * 64 + 64; i += kTdThreads) w_s[i] = i < CL * 64 ? p.w_in[i] : p.b_in[i - CL * 64];
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NCHUNK = (kTdHH * kTdHW + 31) / 32;  // 11
 #pragma unroll 1
-    for (int cg = 0; cg < 4; ++cg)
-    for (int hp = tid; hp < kTdHH * kTdHW; hp += kTdThreads) {
+    for (int wi = warp; wi < 8 * NCHUNK; wi += kTdThreads / 32) {
+        const int cg = wi / NCHUNK, hp = (wi - cg * NCHUNK) * 32 + lane;
+        if (hp >= kTdHH * kTdHW) continue;
         const int ry = hp / kTdHW, rx = hp - ry * kTdHW;
         const int gy = ty0 - 1 + ry, gx = tx0 - 1 + rx;
-        float* ts = tile + (cg * 16) * CS + ry * kTdRS + rx;
+        float* ts = tile + (cg * 8) * CS + ry * kTdRS + rx;
         const bool inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
         if (!inside) {  // zero padding of the 3x3 output convolution
 #pragma unroll
-            for (int c = 0; c < 16; ++c) ts[c * CS] = 0.0f;
+            for (int c = 0; c < 8; ++c) ts[c * CS] = 0.0f;
             continue;
         }
         const size_t go = (size_t)gy * W + gx;
         if (p.intra_in != nullptr) {
-            const float* ip = p.intra_in + ((size_t)b * 64 + cg * 16) * plane + go;
+            const float* ip = p.intra_in + ((size_t)b * 64 + cg * 8) * plane + go;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) ts[c * CS] = __ldg(ip + (size_t)c * plane);
+            for (int c = 0; c < 8; ++c) ts[c * CS] = __ldg(ip + (size_t)c * plane);
             continue;
         }
         // bilinear x2, align_corners=True, with ATen's arithmetic (upsample_bilinear2d: source = scale * dst)
@@ -106,30 +114,41 @@ __global__ void __launch_bounds__(kTdThreads, 2) fpn_topdown_kernel(const __grid
         const int y1 = y0 + (y0 < Hl - 1), x1 = x0 + (x0 < Wl - 1);
         const float ly = fy - (float)y0, lx = fx - (float)x0;
         const float hy = 1.0f - ly, hx = 1.0f - lx;
-        const float* pp = p.prev + ((size_t)b * 64 + cg * 16) * lplane;
+        const float* pp = p.prev + ((size_t)b * 64 + cg * 8) * lplane;
         const size_t o00 = (size_t)y0 * Wl + x0, o01 = (size_t)y0 * Wl + x1;
         const size_t o10 = (size_t)y1 * Wl + x0, o11 = (size_t)y1 * Wl + x1;
-        float l[CL];
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {   // 32 independent taps in flight
+            const float* q = pp + (size_t)c * lplane;
+            v[c] = hy * (hx * __ldg(q + o00) + lx * __ldg(q + o01)) + ly * (hx * __ldg(q + o10) + lx * __ldg(q + o11));
+        }
+        float t[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = 0.0f;
         const float* lp = p.lat + (size_t)b * CL * plane + go;
 #pragma unroll
-        for (int k = 0; k < CL; ++k) l[k] = __ldg(lp + (size_t)k * plane);
+        for (int k = 0; k < CL; ++k) {
+            const float lk = __ldg(lp + (size_t)k * plane);
+            const float4 wa = *reinterpret_cast<const float4*>(w_s + k * 64 + cg * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(w_s + k * 64 + cg * 8 + 4);
+            t[0] = fmaf(wa.x, lk, t[0]); t[1] = fmaf(wa.y, lk, t[1]); t[2] = fmaf(wa.z, lk, t[2]); t[3] = fmaf(wa.w, lk, t[3]);
+            t[4] = fmaf(wb.x, lk, t[4]); t[5] = fmaf(wb.y, lk, t[5]); t[6] = fmaf(wb.z, lk, t[6]); t[7] = fmaf(wb.w, lk, t[7]);
+        }
         const bool interior = p.intra_out != nullptr && ry >= 1 && ry <= kTdTH && rx >= 1 && rx <= kTdTW;
-        float* iop = interior ? p.intra_out + ((size_t)b * 64 + cg * 16) * plane + go : nullptr;
-        const float* wi = p.w_in + cg * 16;
-        const float* bi = p.b_in + cg * 16;
-#pragma unroll 4
-        for (int c = 0; c < 16; ++c) {
-            const float* q = pp + (size_t)c * lplane;
-            const float up = hy * (hx * __ldg(q + o00) + lx * __ldg(q + o01)) + ly * (hx * __ldg(q + o10) + lx * __ldg(q + o11));
-            float t = 0.0f;
+        float* iop = interior ? p.intra_out + ((size_t)b * 64 + cg * 8) * plane + go : nullptr;
 #pragma unroll
-            for (int k = 0; k < CL; ++k) t = fmaf(wi[k * 64 + c], l[k], t);
-            const float v = up + (t + bi[c]);
-            ts[c * CS] = v;
-            if (iop != nullptr) iop[(size_t)c * plane] = v;
+        for (int c = 0; c < 8; ++c) {
+            const float val = v[c] + (t[c] + w_s[CL * 64 + cg * 8 + c]);
+            ts[c * CS] = val;
+            if (iop != nullptr) iop[(size_t)c * plane] = val;
         }
     }
+#endif
     __syncthreads();
+#if defined(MVSTER_TD_SKIP) && MVSTER_TD_SKIP == 2
+    if (tile[threadIdx.x] != 12345.0f) return;
+#endif
 
     // ---- phase 2: 3x3 output convolution from shared memory; a thread owns 1x2 pixels x CO channels for HALF of the
     // 64 input channels (threads 0-127: channels 0-31, threads 128-255: channels 32-63), halves summed through smem ----

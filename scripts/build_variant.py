@@ -13,7 +13,7 @@ from deep_reconstruction_with_epipolar_lines_mvster_b200 import _build as B
 name, defs = sys.argv[1], sys.argv[2:]
 out_dir = os.path.join(ROOT, "variants", "var_" + name)
 os.makedirs(out_dir, exist_ok=True)
-ONLY = ("epi_fwd.cu",)  # the translation units the macros touch; the rest is reused from the main build
+ONLY = tuple(os.environ.get("MVSTER_VARIANT_UNITS", "epi_fwd.cu").split(","))  # units the macros touch; the rest is reused
 
 
 def cc(src):
