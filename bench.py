@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue the 16 launches of a step eagerly instead of replaying them as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-network", action="store_true",
+                    help="skip the secondary whole-network (FPN4 + reg2d + hot path) measurement on rank 0 at N=1")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not pin each rank (N > 1) to the CPUs local to its GPU before allocating pinned buffers")
     ap.add_argument("--cpu-scenes", type=int, default=10, help="timed scenes of the CPU baseline sample")
@@ -221,6 +223,48 @@ def run_cpu_port(args, steps, warmup):
             "ms_per_step": 1e3 * total / steps}
 
 
+def run_network(args, dev):
+    """Images in, 4-stage depth out: checkpoint-compatible MVS4net (random-init weights from the deterministic recipe)
+    with FPN4 / reg2d on this library's direct-convolution and fused kernels + cuDNN for the wide layers, one scene of
+    N views per call.  The reference loader snaps the height to a multiple of 64 (864 -> 832, SURVEY finding 5)."""
+    import deep_reconstruction_with_epipolar_lines_mvster_b200 as mv
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import synthetic as syn
+    h0, w0, n = (args.height // 64) * 64, (args.width // 64) * 64, args.views
+    if h0 < 64 or w0 < 64:
+        return None
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        model = mv.MVS4net(group_cor=True, group_cor_dim=[8, 8, 4, 4], inverse_depth=True, attn_temp=2.0).eval()
+        model.load_state_dict(syn.fill_state_dict(model.state_dict(), seed=7))
+        model = model.to(dev)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        imgs = [torch.rand((1, 3, h0, w0), device=dev, generator=gen) for _ in range(n)]
+        proj = {k: torch.from_numpy(v).to(dev) for k, v in syn.proj_matrices_all_stages(1, n, h0, w0).items()}
+        dv = torch.from_numpy(syn.depth_values(1)).to(dev)
+        with torch.no_grad():
+            for _ in range(3):
+                model(imgs, proj, dv)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            a.record()
+            for _ in range(reps):
+                model(imgs, proj, dv)
+            b.record()
+            torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        del model, imgs
+        torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    return {"value": 1e3 / ms, "unit": UNIT, "ms_per_depth_map": ms,
+            "workload": "MVS4net.forward, images in -> 4-stage depth out, %dx%d N=%d, one scene per call, fp32 "
+                        "(cuDNN TF32 off)" % (h0, w0, n),
+            "what": "FPN4 + reg2d (hand-written direct / fused convolutions + cuDNN for the 32/64-channel layers) "
+                    "around the hot path; secondary number, not part of `value`"}
+
+
 def workload_config(args, world):
     return {"workload": "DTU eval shape N=%d views %dx%d, batch of %d synthetic scenes per GPU (configs[2])"
                         % (args.views, args.height, args.width, args.scenes),
@@ -357,6 +401,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms, k1_ms = (float(x) for x in t.tolist())
 
+    # ---- secondary: the whole MVS4net.forward around the hot path (SURVEY 8d row ii), rank 0 at N=1 only ---------------
+    network = None
+    if rank == 0 and world == 1 and not args.no_network and args.dtype == "fp32":
+        network = run_network(args, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_port(args, args.cpu_scenes, 1)
@@ -390,6 +439,8 @@ def main():
                          "kernel_ms": k1_ms, "fp32_fma_bound_ms": fma_ms,
                          "hbm_bound_ms": alg_bytes / (peak * 1e9) * 1e3},
         }
+        if network is not None:
+            line["whole_network"] = network
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

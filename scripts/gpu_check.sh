@@ -11,7 +11,7 @@ python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit 
 tail -3 gpurun_out/smoke.log
 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"
 tail -2 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
-BCMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1"
+BCMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-network --e2e-steps 1"
 $BCMD > gpurun_out/bench_small.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $BCMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"

@@ -20,7 +20,7 @@ print('NO_TMA', {k:l[k] for k in ('value','ms_per_step')}, l['roofline']['kernel
 PY
 fi
 if [ "${NCU:-0}" = "1" ]; then
-BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1"
+BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-network --e2e-steps 1"
 $BCMD > gpurun_out/bench_small.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:epi_fwd -s 4 -c 4 -f -o gpurun_out/k1_fwd $BCMD > gpurun_out/ncu_k1.log 2>&1
 echo "ncu exit $?"

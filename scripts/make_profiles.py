@@ -29,7 +29,7 @@ for row in csv.DictReader(lines):
     agg.setdefault(key, []).append(v)
 tot = sum(sum(v) / len(v) for v in agg.values())
 with open(os.path.join(out, "%s_launches.md" % tag), "w") as f:
-    f.write("# ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1` (%s)\n\n" % tag)
+    f.write("# ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-network --e2e-steps 1` (%s)\n\n" % tag)
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised launches: compare SHARES.\n")
     f.write("One cascade step = 16 launches of this library (4 stages x schedule/compose/K1/tail).\n\n")
     f.write("| kernel | grid | launches seen | mean µs | share of one step |\n|---|---|---|---|---|\n")
