@@ -10,6 +10,7 @@ from ._lib import EXPORTED_SYMBOLS, launch_count, library_path, load  # noqa: F4
 from .epipolar import EpipolarAggregate, epipolar_aggregate, epipolar_aggregate_variant, epipolar_weights  # noqa: F401
 from .filter import FilterConfig, check_geometric_consistency, filter_scene  # noqa: F401
 from .fusion import depth2pts, fuse_scene, read_pfm, save_pfm, write_ply  # noqa: F401
+from .loss import MVS4net_loss, SinkhornLoss, sinkhorn  # noqa: F401
 from .network import FPN4, GraphedMVS4net, MVS4net, reg2d  # noqa: F401
 from .sharding import bind_to_gpu_numa_node, gpu_local_cpus, rank_world, shard_pairs, shard_round_robin  # noqa: F401
 from .stagenet import (FusedStageNet, depth_regression, homo_warping, init_inverse_range,  # noqa: F401

@@ -41,6 +41,10 @@ _SIGNATURES = {
     "mvster_geo_filter": (c_int, [_P, _P, POINTER(c_double), POINTER(c_double), POINTER(c_int32), c_int, c_int, c_int,
                                   c_double, c_double, c_double, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "mvster_depth2pts": (c_int, [_P, POINTER(c_double), POINTER(c_double), _P, c_int, c_int, _P]),
+    "mvster_sinkhorn_blocks": (c_int, [c_int] * 7),
+    "mvster_sinkhorn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_float, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int,
+                                    c_int, _P]),
+    "mvster_sinkhorn_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "mvster_nchw_to_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 

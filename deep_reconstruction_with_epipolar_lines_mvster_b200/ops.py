@@ -427,3 +427,46 @@ def geo_filter(depths: torch.Tensor, confs: torch.Tensor, ks, es, pairs, condmas
         pr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), v, r, s1 - 1, float(condmask_pixel), float(condmask_depth),
         float(photomask), int(geomask), _ptr(photo), _ptr(geo), _ptr(final), _ptr(avg), _ptr(gsum), h, w, _stream(dz)))
     return photo.bool(), geo.bool(), final.bool(), avg, gsum
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def sinkhorn_fwd(gt_depth: torch.Tensor, hypo: torch.Tensor, attn: torch.Tensor, mask: torch.Tensor, iters: int,
+                 eps: float, continuous: bool, inverse_depth: bool = False, want_grad: bool = True,
+                 want_tmap: bool = False):
+    """Fused Sinkhorn loss (K3).  Returns ``(stats [3], grad_px or None, tmap or None)``.
+
+    ``stats`` = (mean loss over masked pixels, masked-pixel count, range_err_ratio); ``grad_px`` is
+    d(per-pixel loss)/d(attn) (see :func:`sinkhorn_bwd`).  Reference: ``sinkhorn``, models/mvs4net_utils.py:1164-1210.
+    """
+    attn = _f32c(attn, "attn_weight")
+    hypo = _f32c(hypo, "hypo_depth")
+    gt = _f32c(gt_depth, "gt_depth")
+    _require_cuda(mask, "mask")
+    b, d, h, w = attn.shape
+    if tuple(hypo.shape) != (b, d, h, w) or tuple(gt.shape) != (b, h, w) or tuple(mask.shape) != (b, h, w):
+        raise RuntimeError("sinkhorn: expected gt/mask [B,H,W] and hypo/attn [B,D,H,W], got %s %s %s %s" % (
+            tuple(gt.shape), tuple(mask.shape), tuple(hypo.shape), tuple(attn.shape)))
+    m8 = (mask if mask.dtype == torch.bool else mask > 0.5).contiguous().view(torch.uint8)
+    lib = _lib.load()
+    nblocks = lib.mvster_sinkhorn_blocks(b, d, h, w, int(iters), int(bool(continuous)), int(bool(want_grad)))
+    if nblocks <= 0:
+        raise RuntimeError("sinkhorn: unsupported (D=%d, iters=%d); D must be 4 or 8" % (d, iters))
+    dev = attn.device
+    stats = torch.empty(3, device=dev, dtype=torch.float32)
+    partials = torch.empty(3 * nblocks, device=dev, dtype=torch.float64)
+    grad_px = torch.empty_like(attn) if want_grad else None
+    tmap = torch.empty((b, h * w, d, d + (1 if continuous else 0)), device=dev, dtype=torch.float32) if want_tmap else None
+    _lib.check(lib.mvster_sinkhorn_fwd(_ptr(gt), _ptr(hypo), _ptr(attn), _ptr(m8), int(iters), float(eps),
+                                       int(bool(continuous)), int(bool(inverse_depth)), _ptr(stats), _ptr(grad_px),
+                                       _ptr(tmap), _ptr(partials), b, d, h, w, _stream(attn)))
+    return stats, grad_px, tmap
+
+
+def sinkhorn_bwd(grad_px: torch.Tensor, stats: torch.Tensor, grad_loss: torch.Tensor) -> torch.Tensor:
+    """``grad_attn = grad_px * grad_loss / count`` (the mean over masked pixels), on the device without a sync."""
+    b, d, h, w = grad_px.shape
+    gl = _f32c(grad_loss.reshape(1), "grad_loss")
+    out = torch.empty_like(grad_px)
+    _lib.check(_lib.load().mvster_sinkhorn_bwd(_ptr(grad_px), _ptr(stats), _ptr(gl), _ptr(out), b, d, h, w,
+                                               _stream(grad_px)))
+    return out

@@ -209,6 +209,30 @@ int mvster_geo_filter(const float* depths, const float* confs, const double* K, 
  */
 int mvster_depth2pts(const float* depth, const double* K, const double* E, double* xyz, int H, int W, void* stream);
 
+/* ---- K3: fused Sinkhorn / Wasserstein depth loss ----------------------------------------
+ * Replaces `sinkhorn(gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous)` (models/mvs4net_utils.py:
+ * 1164-1210) as called per stage by MVS4net_loss / Blend_loss (models/MVS4Net.py:234, :281), together with the
+ * `range_err_ratio` statistic next to that call (:225-232).  One thread per pixel runs the 2*iters log-domain scaling
+ * passes on its D x D(+1) problem in registers AND the backward sweep of the unrolled iterations, so the call returns
+ * the loss and d(loss)/d(attn_weight); the reference's [B,HW,D,D] tensors never exist.
+ *   gt_depth dev [B,H,W] fp32; hypo, attn dev [B,D,H,W] fp32; mask dev [B,H,W] uint8 (the reference's `mask > 0.5`)
+ *   iters, eps, continuous: as in the reference (train_mvs4.py:73-75: --ot_iter, --ot_eps, --ot_continous)
+ *   inverse_depth: selects the 1/depth form of range_err_ratio (models/MVS4Net.py:226-228)
+ *   stats    dev [3] fp32, written: mean loss over masked pixels (NaN if none, like torch), masked count, range_err_ratio
+ *   grad_px  dev [B,D,H,W] fp32, optional (NULL ok): d(per-pixel loss)/d(attn), zero at unmasked pixels;
+ *            mvster_sinkhorn_bwd turns it into the gradient of the mean
+ *   tmap     dev [B,H*W,D,D(+1)] fp32, optional (NULL ok): the transport map T_map (first return value of the reference)
+ *   partials dev workspace of 3 * mvster_sinkhorn_blocks(...) doubles (deterministic two-pass reduction, no atomics)
+ * D in {4, 8}.  mvster_sinkhorn_blocks returns 0 when (D, iters) does not fit the in-kernel backward.
+ */
+int mvster_sinkhorn_blocks(int B, int D, int H, int W, int iters, int continuous, int want_grad);
+int mvster_sinkhorn_fwd(const float* gt_depth, const float* hypo, const float* attn, const uint8_t* mask, int iters,
+                        float eps, int continuous, int inverse_depth, float* stats, float* grad_px, float* tmap,
+                        double* partials, int B, int D, int H, int W, void* stream);
+/* grad_attn[i] = grad_px[i] * grad_loss[0] / stats[1]   (grad_loss dev [1]: upstream gradient of the scalar loss) */
+int mvster_sinkhorn_bwd(const float* grad_px, const float* stats, const float* grad_loss, float* grad_attn, int B,
+                        int D, int H, int W, void* stream);
+
 /* ---- layout helper: NCHW fp32 -> NHWC fp32/bf16 (the FPN emits NCHW, models/mvs4net_utils.py:504-507) ----- */
 int mvster_nchw_to_nhwc(const float* in, void* out, int B, int C, int H, int W, int out_dtype, void* stream);
 

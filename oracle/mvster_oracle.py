@@ -529,3 +529,123 @@ def cascade_port(features, projs, depth_values, logits, groups, ndepths, split_i
                "inverse_min_depth": 1 / depth + split_itv[s] * last_itv,
                "inverse_max_depth": 1 / depth - split_itv[s] * last_itv}
     return out["depth"], out["photometric_confidence"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K3: Sinkhorn / Wasserstein depth loss                     models/mvs4net_utils.py:1164-1210, models/MVS4Net.py:225-234
+# ---------------------------------------------------------------------------------------------------------------
+def _logsumexp_np(x: np.ndarray, axis: int) -> np.ndarray:
+    m = np.max(x, axis=axis, keepdims=True)
+    m = np.where(np.isfinite(m), m, 0.0)
+    return (np.log(np.sum(np.exp(x - m), axis=axis, keepdims=True)) + m).squeeze(axis)
+
+
+def sinkhorn_np(gt_depth: np.ndarray, hypo_depth: np.ndarray, attn_weight: np.ndarray, mask: np.ndarray, iters: int,
+                eps: float = 1.0, continuous: bool = False, inverse_depth: bool = False, dtype=np.float64):
+    """float64 restatement of ``sinkhorn`` (models/mvs4net_utils.py:1164-1210) with the analytic gradient.
+
+    Inputs keep the reference's layouts: gt/mask [B,H,W], hypo/attn [B,D,H,W].  Returns a dict with
+      ``T_map`` [B,HW,D,NC], ``loss`` (mean over masked pixels, :1208), ``grad_attn`` [B,D,H,W] = d loss / d attn_weight
+      (what autograd yields for the reference), ``count`` and ``range_err_ratio`` (models/MVS4Net.py:225-232).
+    Quirk kept: the cost enters the exponent with a positive sign (``D_map/eps``, :1200-1204).
+    """
+    gt = np.asarray(gt_depth, dtype=np.float32)
+    hypo32 = np.asarray(hypo_depth, dtype=np.float32)
+    b, d, h, w = hypo32.shape
+    msk = np.asarray(mask).astype(bool)
+    ar = np.arange(d)
+    if not continuous:
+        cost = np.abs(ar[:, None] - ar[None, :]).astype(dtype)                              # :1173
+        cost = np.broadcast_to(cost, (b, h * w, d, d)).copy()                               # :1174
+        gi = np.abs(hypo32 - gt[:, None]).argmin(1).reshape(b, h * w)                       # :1175 (fp32 like the ref)
+        gt_dist = np.zeros((b, h * w, d), dtype=dtype)                                      # :1176-1178
+        np.put_along_axis(gt_dist, gi[..., None], 1.0, axis=2)
+    else:
+        gt_dist = np.zeros((b, h * w, d + 1), dtype=dtype)                                  # :1180-1181
+        gt_dist[:, :, -1] = 1
+        cost = np.zeros((b, h, w, d, d + 1), dtype=dtype)                                   # :1182-1184
+        cost[..., :d, :d] = np.abs(ar[:, None] - ar[None, :])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            itv = np.float32(1) / hypo32[:, 2] - np.float32(1) / hypo32[:, 1]               # :1185 (fp32 like the ref)
+            gbd = (np.float32(1) / gt - np.float32(1) / hypo32[:, 0]) / itv                 # :1186
+        gbd[~msk] = 10                                                                      # :1188
+        cost[..., -1] = np.abs(gbd[..., None].astype(dtype) - ar)                           # :1190-1191
+        cost = cost.reshape(b, h * w, d, d + 1)                                             # :1192
+    pred = np.transpose(np.asarray(attn_weight, dtype=np.float32), (0, 2, 3, 1)).reshape(b, h * w, d)   # :1194
+    # the +1e-12 is an fp32 addition in the reference; keep it so that log(1 + 1e-12) == 0 exactly
+    log_mu = np.log((gt_dist.astype(np.float32) + np.float32(1e-12)).astype(dtype))         # :1197
+    at = (pred + np.float32(1e-12)).astype(dtype)
+    log_nu = np.log(at)                                                                     # :1198
+    kmat = cost / dtype(eps)
+    u = np.zeros_like(log_nu)
+    v = np.zeros_like(log_mu)
+    lus, lvs = [], []
+    for _ in range(iters):                                                                  # :1201-1204
+        lv = _logsumexp_np(kmat + u[..., :, None], axis=2)
+        v = log_mu - lv
+        lu = _logsumexp_np(kmat + v[..., None, :], axis=3)
+        u = log_nu - lu
+        lus.append(lu)
+        lvs.append(lv)
+    tmap = np.exp(kmat + u[..., :, None] + v[..., None, :])                                 # :1207
+    per_px = (tmap * cost).reshape(b * h * w, -1).sum(-1)
+    sel = msk.reshape(-1)
+    count = int(sel.sum())
+    loss = per_px[sel].mean() if count else float("nan")                                    # :1208
+    # reverse sweep of the unrolled iterations
+    g = tmap * cost
+    gu, gv = g.sum(3), g.sum(2)
+    gl = np.zeros_like(log_nu)
+    for t in range(iters - 1, -1, -1):
+        gl += gu
+        vt = log_mu - lvs[t]
+        gv = gv - np.einsum("bpi,bpij->bpj", gu, np.exp(kmat + vt[..., None, :] - lus[t][..., :, None]))
+        up = (log_nu - lus[t - 1]) if t > 0 else np.zeros_like(log_nu)
+        gu = -np.einsum("bpj,bpij->bpi", gv, np.exp(kmat + up[..., :, None] - lvs[t][..., None, :]))
+        gv = np.zeros_like(gv)
+    grad = gl / at
+    grad = grad * sel.reshape(b, h * w, 1) / max(count, 1)
+    grad = np.transpose(grad.reshape(b, h, w, d), (0, 3, 1, 2))
+    # out-of-range statistic                                                              models/MVS4Net.py:225-232
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if inverse_depth:
+            ditv = np.abs(np.float32(1) / hypo32[:, 2] - np.float32(1) / hypo32[:, 1])
+            oor = (np.abs(np.float32(1) / hypo32 - (np.float32(1) / gt)[:, None]) <= ditv[:, None]).sum(1) == 0
+        else:
+            ditv = np.abs(hypo32[:, 2] - hypo32[:, 1])
+            oor = (np.abs(hypo32 - gt[:, None]) <= ditv[:, None]).sum(1) == 0
+    ratio = float(oor[msk].astype(np.float32).mean()) if count else float("nan")
+    return {"T_map": tmap, "loss": float(loss), "grad_attn": grad, "count": count, "range_err_ratio": ratio}
+
+
+def sinkhorn_port(gt_depth, hypo_depth, attn_weight, mask, iters, eps=1.0, continuous=False):
+    """fp32 torch-CPU port with the reference's own op sequence (materialised [B,HW,D,D(+1)] tensors, 2*iters
+    ``torch.logsumexp`` passes, autograd for the gradient) - the timed CPU baseline of K3.  Returns (T_map, loss)."""
+    b, d, h, w = attn_weight.shape
+    dev = attn_weight.device
+    ar = torch.arange(d, dtype=torch.float32, device=dev)
+    base = (ar[:, None] - ar[None, :]).abs()
+    if not continuous:
+        cost = base[None, None].repeat(b, h * w, 1, 1)
+        gi = (hypo_depth - gt_depth[:, None]).abs().min(1)[1].reshape(b * h * w, 1)
+        gt_dist = torch.zeros(b * h * w, d, device=dev).scatter_add_(1, gi, torch.ones(b * h * w, 1, device=dev)).reshape(b, h * w, d)
+    else:
+        gt_dist = torch.zeros(b, h * w, d + 1, device=dev)
+        gt_dist[:, :, -1] = 1
+        cost = torch.zeros(b, d, d + 1, device=dev)
+        cost[:, :d, :d] = base
+        cost = cost[:, None, None].repeat(1, h, w, 1, 1)
+        itv = 1 / hypo_depth[:, 2] - 1 / hypo_depth[:, 1]
+        gbd = (1 / gt_depth - 1 / hypo_depth[:, 0]) / itv
+        gbd[~mask] = 10
+        cost[..., -1] = torch.stack([(gbd - i).abs() for i in range(d)], dim=1).permute(0, 2, 3, 1)
+        cost = cost.reshape(b, h * w, d, d + 1)
+    pred = attn_weight.permute(0, 2, 3, 1).reshape(b, h * w, d)
+    log_mu, log_nu = (gt_dist + 1e-12).log(), (pred + 1e-12).log()
+    u, v = torch.zeros_like(log_nu), torch.zeros_like(log_mu)
+    for _ in range(iters):
+        v = log_mu - torch.logsumexp(cost / eps + u.unsqueeze(3), dim=2)
+        u = log_nu - torch.logsumexp(cost / eps + v.unsqueeze(2), dim=3)
+    tmap = (cost / eps + u.unsqueeze(3) + v.unsqueeze(2)).exp()
+    loss = (tmap * cost).reshape(b * h * w, -1)[mask.reshape(-1)].sum(-1).mean()
+    return tmap, loss

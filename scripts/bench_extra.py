@@ -415,15 +415,61 @@ def bench_scene(args, dev):
                               "the timing does not depend on it"}))
 
 
+def bench_sinkhorn(args, dev):
+    """K3: the four per-stage OT losses of one training step (512x640, B=2, ndepths 8-8-4-4, train_mvs4.py default
+    ot_iter=10, eps=1): fused loss+gradient kernel vs the reference's op sequence in eager PyTorch on the same GPU
+    (oracle port: [B,HW,D,D] tensors, 2*iters logsumexp passes, autograd backward)."""
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import loss as L
+    from oracle import mvster_oracle as O
+    gen = torch.Generator(device=dev).manual_seed(11)
+    stages = []
+    for d, h, w in ((8, 64, 80), (8, 128, 160), (4, 256, 320), (4, 512, 640)):
+        hypo = torch.sort(500 + 300 * torch.rand(2, d, h, w, device=dev, generator=gen), dim=1, descending=True)[0]
+        gt = 450 + 400 * torch.rand(2, h, w, device=dev, generator=gen)
+        attn = torch.softmax(torch.randn(2, d, h, w, device=dev, generator=gen), 1).requires_grad_(True)
+        mask = torch.rand(2, h, w, device=dev, generator=gen) > 0.2
+        stages.append((gt, hypo, attn, mask))
+    out = {"bench": "sinkhorn_loss_4stages_fwd_bwd", "config": "512x640 B=2 ndepths 8-8-4-4 ot_iter=10 eps=1 fp32"}
+
+    def fused():
+        for gt, hypo, attn, mask in stages:
+            attn.grad = None
+            L.SinkhornLoss.apply(gt, hypo, attn, mask, 10, 1.0, False, True)[0].backward()
+
+    def eager():
+        for gt, hypo, attn, mask in stages:
+            attn.grad = None
+            O.sinkhorn_port(gt, hypo, attn, mask, 10, 1.0, False)[1].backward()
+
+    out["fused_ms"] = timed(fused, args.iters)
+    torch.cuda.reset_peak_memory_stats()
+    fused()
+    out["fused_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
+    out["eager_ms"] = timed(eager, max(3, args.iters // 4))
+    torch.cuda.reset_peak_memory_stats()
+    eager()
+    out["eager_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
+    out["speedup"] = out["eager_ms"] / out["fused_ms"]
+    gt, hypo, attn, mask = stages[3]
+    ms4 = timed(lambda: ops.sinkhorn_fwd(gt, hypo, attn.detach(), mask, 10, 1.0, False, True), args.iters)
+    px = gt.numel()
+    # per pixel and iteration: 2*D*D exp + 2*D log forward, 2*D*D exp backward (D = 4), plus D*D for the transport map
+    mufu = px * (10 * (4 * 4 * 4 + 2 * 4) + 4 * 4 + 4)
+    out["stage4_kernel_ms"] = ms4
+    out["stage4_Gtranscendental_per_s"] = mufu / ms4 / 1e6
+    out["stage4_frac_of_xu_peak"] = (mufu / ms4 / 1e6) / (148 * 16 * 1.92)   # 16 MUFU/clk/SM at 1.92 GHz
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network,config0,scene")
+    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network,config0,scene,sinkhorn")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--cpu-filter-pairs", type=int, default=20)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     fns = {"stages": bench_stages, "binpick": bench_binpick, "train": bench_train, "filter": bench_filter,
-           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network, "config0": bench_config0, "scene": bench_scene}
+           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network, "config0": bench_config0, "scene": bench_scene, "sinkhorn": bench_sinkhorn}
     for name in args.which.split(","):
         fns[name](args, dev)
 
