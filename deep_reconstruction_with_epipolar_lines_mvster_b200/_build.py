@@ -38,7 +38,7 @@ def _sources():
 
 def _digest(path: str) -> str:
     h = hashlib.sha1()
-    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "epi_common.cuh"), os.path.join(CSRC, "tail_common.cuh"),
+    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "epi_common.cuh"), os.path.join(CSRC, "epi_tma.cuh"), os.path.join(CSRC, "tail_common.cuh"),
                 os.path.join(INCLUDE, "mvster_b200.h")]:
         with open(dep, "rb") as f:
             h.update(f.read())

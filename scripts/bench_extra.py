@@ -116,6 +116,17 @@ def bench_train(args, dev):
 
         out["stage%d_fwd_bwd_ms" % (stage + 1)] = timed(step, args.iters)
         out["stage%d_fwd_ms" % (stage + 1)] = timed(fwd_only, args.iters)
+        # the backward launch alone (C-ABI call + the zero-fill of grad_src it scatters into), and its HBM roofline:
+        # SURVEY 8d bytes = grad_out + ref + src + hypo read, grad_ref + grad_src written (+ out, wsum re-read here)
+        with torch.no_grad():
+            nh = [ops.to_nhwc(f.detach()) for f in feats]
+            rt = ops.compose_homographies(proj)
+            vol, wsum, _ = ops.epi_fwd(nh[0], nh[1:], rt, hypo, g, 2.0, want_wsum=True)
+            ms = timed(lambda: ops.epi_bwd(nh[0], nh[1:], rt, hypo, vol, wsum, gout, g, 2.0), args.iters)
+        px = 2 * h * w
+        alg = px * (4 * g * d * 2 + 4 * d * 2 + 5 * c * 4 * 2)
+        out["stage%d_bwd_call_ms" % (stage + 1)] = ms
+        out["stage%d_bwd_frac_hbm_roofline" % (stage + 1)] = alg / (HBM * 1e6) / ms
     out["bench"] = "train_k1_fwd_bwd"
     out["config"] = "512x640 B=2 N=5 fp32, EpipolarAggregate autograd (includes layout views, zero-init of grads)"
     print(json.dumps(out))
@@ -461,15 +472,67 @@ def bench_sinkhorn(args, dev):
     print(json.dumps(out))
 
 
+def bench_train_step(args, dev):
+    """BASELINE configs[3] widened to the whole network: one training step (MVS4net.train() forward, MVS4net_loss with
+    ot_iter=10, backward, Adam) at the DTU-train shape 512x640, B=2, N=5, fp32 - the B200 path (fused K1 fwd/bwd, tail
+    fwd/bwd, fused Sinkhorn loss; cuDNN convolutions) vs the reference's op sequence in eager PyTorch on the same GPU."""
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import loss as L
+    from oracle import mvster_oracle as O
+    h0, w0, n, b = 512, 640, 5, 2
+    torch.backends.cudnn.allow_tf32 = False
+    model = mv.MVS4net(**NET_CFG).train()
+    model.load_state_dict(syn.fill_state_dict(model.state_dict(), seed=7))
+    model = model.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    imgs = [torch.rand((b, 3, h0, w0), device=dev, generator=gen) for _ in range(n)]
+    proj = {k: torch.from_numpy(v).to(dev) for k, v in syn.proj_matrices_all_stages(b, n, h0, w0).items()}
+    dv = torch.from_numpy(syn.depth_values(b)).to(dev)
+    gts, masks = {}, {}
+    for s in range(4):
+        h, w = h0 >> (3 - s), w0 >> (3 - s)
+        gts["stage%d" % (s + 1)] = 560 + 300 * torch.rand((b, h, w), device=dev, generator=gen)
+        masks["stage%d" % (s + 1)] = (torch.rand((b, h, w), device=dev, generator=gen) > 0.2).float()
+    kw = dict(stage_lw=[1, 1, 1, 1], l1ot_lw=[0, 1], inverse_depth=True, ot_iter=10, ot_eps=1, ot_continous=False)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    fused_stagenet = model.stagenet
+
+    def eager_loss(out):
+        total = 0.0
+        for k in out:
+            total = total + O.sinkhorn_port(gts[k], out[k]["hypo_depth"], out[k]["attn_weight"], masks[k] > 0.5, 10, 1.0)[1]
+        return total
+
+    def step(eager):
+        opt.zero_grad(set_to_none=True)
+        out = model(imgs, proj, dv)
+        total = eager_loss(out) if eager else L.MVS4net_loss(out, gts, masks, **kw)[0]
+        total.backward()
+        opt.step()
+
+    res = {"bench": "train_step_mvs4net_512x640_b2_n5", "config": "fwd + OT loss (10 iters) + bwd + Adam, fp32 (TF32 off)"}
+    its = max(3, args.iters // 4)
+    for name, eager in (("b200", False), ("eager_reference_like", True)):
+        model.stagenet = _EagerStagenet() if eager else fused_stagenet
+        torch.cuda.reset_peak_memory_stats()
+        res[name + "_ms"] = timed(lambda: step(eager), its)
+        res[name + "_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
+    model.stagenet = fused_stagenet
+    res["samples_per_s_b200"] = 1e3 * b / res["b200_ms"]
+    res["speedup"] = res["eager_reference_like_ms"] / res["b200_ms"]
+    print(json.dumps(res))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network,config0,scene,sinkhorn")
+    ap.add_argument("--which", default="stages,binpick,train,filter,ref_gpu,ref_gpu_train,network,config0,scene,sinkhorn,train_step")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--cpu-filter-pairs", type=int, default=20)
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="let cuDNN auto-tune its algorithm per shape")
     args = ap.parse_args()
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
     dev = torch.device("cuda", 0)
     fns = {"stages": bench_stages, "binpick": bench_binpick, "train": bench_train, "filter": bench_filter,
-           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network, "config0": bench_config0, "scene": bench_scene, "sinkhorn": bench_sinkhorn}
+           "ref_gpu": bench_ref_gpu, "ref_gpu_train": bench_ref_gpu_train, "network": bench_network, "config0": bench_config0, "scene": bench_scene, "sinkhorn": bench_sinkhorn, "train_step": bench_train_step}
     for name in args.which.split(","):
         fns[name](args, dev)
 
