@@ -306,24 +306,9 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB)
 #pragma unroll
         for (int q = 0; q < 4; ++q) { rf[q] = mul2(r.q[q], sc); gref[q] = pack2(0.0f, 0.0f); }
     }
-    float hyp[D], dS[D], dA[GPL][D];
+    float hyp[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + d) * plane + pix_off);
-        const float inv_s = 1.0f / ldg_stream(p.wsum + ((size_t)b * D + d) * plane + pix_off);
-        float part = 0.0f;
-#pragma unroll
-        for (int g = 0; g < GPL; ++g) {
-            const size_t o = (((size_t)b * G + sub * GPL + g) * D + d) * plane + pix_off;
-            const float go = live ? ldg_stream(p.gout + o) : 0.0f;
-            const float ov = ldg_stream(p.out + o);
-            dA[g][d] = go * inv_s;
-            part = fmaf(go, ov, part);
-        }
-#pragma unroll
-        for (int m = 1; m < L; m <<= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-        dS[d] = -part * inv_s;
-    }
+    for (int d = 0; d < D; ++d) hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + d) * plane + pix_off);
 
     const float fxp = (float)x, fyp = (float)y;
     const float wlim = (float)p.Ws, hlim = (float)p.Hs;
@@ -367,7 +352,25 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB)
         }
     };
 
-    stage_view(0);
+    stage_view(0);  // needs the hypotheses only: the first box is in flight while the gradient planes are read
+
+    float dS[D], dA[GPL][D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float inv_s = 1.0f / ldg_stream(p.wsum + ((size_t)b * D + d) * plane + pix_off);
+        float part = 0.0f;
+#pragma unroll
+        for (int g = 0; g < GPL; ++g) {
+            const size_t o = (((size_t)b * G + sub * GPL + g) * D + d) * plane + pix_off;
+            const float go = live ? ldg_stream(p.gout + o) : 0.0f;
+            const float ov = ldg_stream(p.out + o);
+            dA[g][d] = go * inv_s;
+            part = fmaf(go, ov, part);
+        }
+#pragma unroll
+        for (int m = 1; m < L; m <<= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+        dS[d] = -part * inv_s;
+    }
 
 #pragma unroll 1
     for (int v = 0; v < p.Nsrc; ++v) {
@@ -479,6 +482,8 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB)
         // stay in the same 2x2 texel cell (sub-texel hypothesis spacing at the fine stages) accumulate in registers
         // and are reduced once per cell instead of once per hypothesis.
         f32x2 aL0[4], aL1[4], aR0[4], aR1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aL0[q] = aL1[q] = aR0[q] = aR1[q] = pack2(0.0f, 0.0f);
         bool fL0 = false, fL1 = false, fR0 = false, fR1 = false;
         int px0 = 0, py0 = 0;
         auto flush = [&]() {
@@ -548,6 +553,8 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB)
             if (d > 0 && (x0 != px0 || y0 != py0)) {
                 flush();
                 fL0 = fL1 = fR0 = fR1 = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) aL0[q] = aL1[q] = aR0[q] = aR1[q] = pack2(0.0f, 0.0f);
             }
             px0 = x0; py0 = y0;
             const f32x2 pl0 = pack2(wl0, wl0), pl1 = pack2(wl1, wl1), pt0 = pack2(tk0, tk0), pt1 = pack2(tk1, tk1);
@@ -557,12 +564,10 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB)
                 float lo, hi;
                 unpack2(dwp[q], lo, hi);
                 const f32x2 prv = pack2(__shfl_up_sync(0xffffffffu, lo, L), __shfl_up_sync(0xffffffffu, hi, L));
-                const f32x2 cl0 = fma2(pl0, dwp[q], mul2(pt0, prv)), cl1 = fma2(pl1, dwp[q], mul2(pt1, prv));
-                const f32x2 cr0 = mul2(pr0, dwp[q]), cr1 = mul2(pr1, dwp[q]);
-                aL0[q] = fL0 ? add2(aL0[q], cl0) : cl0;
-                aL1[q] = fL1 ? add2(aL1[q], cl1) : cl1;
-                aR0[q] = fR0 ? add2(aR0[q], cr0) : cr0;
-                aR1[q] = fR1 ? add2(aR1[q], cr1) : cr1;
+                aL0[q] = fma2(pl0, dwp[q], fma2(pt0, prv, aL0[q]));
+                aL1[q] = fma2(pl1, dwp[q], fma2(pt1, prv, aL1[q]));
+                aR0[q] = fma2(pr0, dwp[q], aR0[q]);
+                aR1[q] = fma2(pr1, dwp[q], aR1[q]);
             }
             // a column is live once it has received a non-zero (hence in-bounds) weight; later zero-weight samples of
             // the same cell add exact zeros
