@@ -33,6 +33,9 @@ _SIGNATURES = {
     "mvster_tail": (c_int, [_P, _P, c_float, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "mvster_regtail": (c_int, [_P, _P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "mvster_conv3d_small": (c_int, [_P, _P, _P, _P, _P] + [c_int] * 9 + [_P]),
+    "mvster_conv3d_small_slice": (c_int, [_P, _P, _P, _P, _P] + [c_int] * 10 + [_P]),
+    "mvster_conv2d_mid5": (c_int, [_P, _P, _P, _P] + [c_int] * 6 + [_P]),
+    "mvster_conv3d_mid": (c_int, [_P, _P, _P, _P] + [c_int] * 8 + [_P]),
     "mvster_conv2d_small": (c_int, [_P, _P, _P, _P] + [c_int] * 10 + [_P]),
     "mvster_fpn_topdown": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),
     "mvster_tail_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),

@@ -277,6 +277,215 @@ __global__ void __launch_bounds__(128, 3) conv5s2_kernel(const __grid_constant__
     }
 }
 
+// ---- 32/64-channel stride-1 layers (reg2d conv4 / conv6, FPN4 conv3.1 / conv3.2) ---------------------------------------
+// Their filter banks (110 .. 442 KB) do not fit the kernel-parameter space, and slicing them into <= 32 KB launches
+// leaves each launch with a fraction of a wave at 1/4 .. 1/8 resolution.  Here the folded weights stay in global memory
+// as [kd][ky][kx][ci][co]: a thread owns 2x2 output pixels x 16 output channels, blockIdx.z enumerates (batch, depth,
+// 16-channel slice) so that ONE launch covers every output channel, and the 16 weights of a (tap, ci) are four
+// CTA-uniform 16-byte loads (one L1 transaction per warp) feeding 64 FFMAs.
+template <int KD, int CIN>
+struct MidConvParams {
+    const float* x;
+    const float* w;     // dev [KD][3][3][CIN][co_total]
+    const float* bias;  // dev [co_total]
+    float* y;
+    int B, D, H, W, relu, co_total;
+};
+
+template <int KD, int CIN>
+__global__ void __launch_bounds__(128, 2) midconv_s1_kernel(const MidConvParams<KD, CIN> p) {
+    constexpr int COT = 16;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int nsl = p.co_total / COT;
+    const int sl = blockIdx.z % nsl, bd = blockIdx.z / nsl;
+    const int b = bd / p.D, d = bd % p.D;
+    const int H = p.H, W = p.W;
+    if (2 * i >= W || 2 * j >= H) return;
+    const int x0 = 2 * i, y0 = 2 * j;
+    const size_t plane = (size_t)H * W;
+    float acc[2][2][COT];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int co = 0; co < COT; ++co) acc[a][c][co] = 0.0f;
+    const bool vl = x0 > 0, vr = x0 + 2 < W;
+    bool vy[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vy[r] = (unsigned)(y0 - 1 + r) < (unsigned)H;
+#pragma unroll 1
+    for (int kd = 0; kd < KD; ++kd) {
+        const int dz = d + kd - KD / 2;
+        if ((unsigned)dz >= (unsigned)p.D) continue;
+        const float* xp = p.x + (((size_t)b * CIN) * p.D + dz) * plane + (size_t)(y0 - 1) * W + x0;
+        const float* wk = p.w + ((size_t)kd * 9 * CIN) * p.co_total + sl * COT;
+#pragma unroll 1
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* q = xp + (size_t)ci * p.D * plane;
+            float in[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float* qr = q + (size_t)r * W;
+                const float2 m = ldz2(qr, vy[r]);
+                in[r][0] = ldz(qr - 1, vy[r] && vl);
+                in[r][1] = m.x;
+                in[r][2] = m.y;
+                in[r][3] = ldz(qr + 2, vy[r] && vr);
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4* wq = reinterpret_cast<const float4*>(wk + ((size_t)(ky * 3 + kx) * CIN + ci) * p.co_total);
+#pragma unroll
+                    for (int k = 0; k < COT / 4; ++k) {
+                        const float4 w4 = __ldg(wq + k);
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int co = 4 * k + e;
+                            acc[0][0][co] = fmaf(wv[e], in[ky][kx], acc[0][0][co]);
+                            acc[0][1][co] = fmaf(wv[e], in[ky][kx + 1], acc[0][1][co]);
+                            acc[1][0][co] = fmaf(wv[e], in[ky + 1][kx], acc[1][0][co]);
+                            acc[1][1][co] = fmaf(wv[e], in[ky + 1][kx + 1], acc[1][1][co]);
+                        }
+                    }
+                }
+        }
+    }
+    float* yp = p.y + (((size_t)b * p.co_total + sl * COT) * p.D + d) * plane + (size_t)y0 * W + x0;
+#pragma unroll
+    for (int co = 0; co < COT; ++co) {
+        const float bv = __ldg(p.bias + sl * COT + co);
+        float v[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                v[a][c] = acc[a][c][co] + bv;
+                if (p.relu) v[a][c] = fmaxf(v[a][c], 0.0f);
+            }
+        float* yc = yp + (size_t)co * p.D * plane;
+        *reinterpret_cast<float2*>(yc) = make_float2(v[0][0], v[0][1]);
+        *reinterpret_cast<float2*>(yc + W) = make_float2(v[1][0], v[1][1]);
+    }
+}
+
+template <int KD, int CIN>
+static int launch_mid(const float* x, const float* w, const float* bias, float* y, int B, int Cout, int D, int H, int W,
+                      int relu, cudaStream_t s) {
+    MidConvParams<KD, CIN> p{x, w, bias, y, B, D, H, W, relu, Cout};
+    const long long z = (long long)B * D * (Cout / 16);
+    if (z > 65535) return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_mid: B*D*Cout/16 too large");
+    dim3 grid((W / 2 + 31) / 32, (H / 2 + 3) / 4, (unsigned)z);
+    midconv_s1_kernel<KD, CIN><<<grid, 128, 0, s>>>(p);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("conv3d_mid launch");
+    return MVSTER_OK;
+}
+
+// ---- 5x5 stride-2 layers with device-resident weights (FPN4 conv1.0 / conv2.0 / conv3.0) --------------------------------
+// ncu on conv5s2_kernel: with a 25 KB filter bank in the kernel-parameter space the constant cache thrashes (issue
+// 15-35 %).  Same recipe as midconv_s1_kernel instead: weights [ky][kx][ci][co] in global memory read as CTA-uniform
+// 16-byte loads, a thread owns 2x2 output pixels x 16 output channels (1600 FFMAs per input channel for 21 input and
+// 100 weight loads), blockIdx.z enumerates (batch, 16-channel slice).
+template <int CIN>
+struct MidConv5Params {
+    const float* x;
+    const float* w;     // dev [5][5][CIN][co_total]
+    const float* bias;  // dev [co_total]
+    float* y;
+    int B, H, W, relu, co_total;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(128, 2) midconv5s2_kernel(const MidConv5Params<CIN> p) {
+    constexpr int COT = 16;
+    const int Ho = p.H / 2, Wo = p.W / 2;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int nsl = p.co_total / COT;
+    const int sl = blockIdx.z % nsl, b = blockIdx.z / nsl;
+    if (2 * i >= Wo || 2 * j >= Ho) return;
+    const int H = p.H, W = p.W;
+    const int xi = 4 * i, yi = 4 * j;  // outputs (2j..2j+1, 2i..2i+1) read input rows yi-2..yi+4, columns xi-2..xi+4
+    const size_t plane = (size_t)H * W, oplane = (size_t)Ho * Wo;
+    float acc[2][2][COT];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int co = 0; co < COT; ++co) acc[a][c][co] = 0.0f;
+    bool vy[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) vy[r] = (unsigned)(yi - 2 + r) < (unsigned)H;
+    const bool vl = xi > 0, vr = xi + 4 < W;
+    const float* xp = p.x + ((size_t)b * CIN) * plane + (size_t)(yi - 2) * W + xi;
+    const float* wk = p.w + sl * COT;
+#pragma unroll 1
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* q = xp + (size_t)ci * plane;
+        float in[7][7];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const float* qr = q + (size_t)r * W;
+            const float2 l = ldz2(qr - 2, vy[r] && vl);
+            const float4 m = ldz4(qr, vy[r]);
+            in[r][0] = l.x; in[r][1] = l.y; in[r][2] = m.x; in[r][3] = m.y; in[r][4] = m.z; in[r][5] = m.w;
+            in[r][6] = ldz(qr + 4, vy[r] && vr);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const float4* wq = reinterpret_cast<const float4*>(wk + ((size_t)(ky * 5 + kx) * CIN + ci) * p.co_total);
+#pragma unroll
+                for (int k = 0; k < COT / 4; ++k) {
+                    const float4 w4 = __ldg(wq + k);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int co = 4 * k + e;
+                        acc[0][0][co] = fmaf(wv[e], in[ky][kx], acc[0][0][co]);
+                        acc[0][1][co] = fmaf(wv[e], in[ky][kx + 2], acc[0][1][co]);
+                        acc[1][0][co] = fmaf(wv[e], in[ky + 2][kx], acc[1][0][co]);
+                        acc[1][1][co] = fmaf(wv[e], in[ky + 2][kx + 2], acc[1][1][co]);
+                    }
+                }
+            }
+    }
+    float* yp = p.y + ((size_t)b * p.co_total + sl * COT) * oplane + (size_t)(2 * j) * Wo + 2 * i;
+#pragma unroll
+    for (int co = 0; co < COT; ++co) {
+        const float bv = __ldg(p.bias + sl * COT + co);
+        float v[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                v[a][c] = acc[a][c][co] + bv;
+                if (p.relu) v[a][c] = fmaxf(v[a][c], 0.0f);
+            }
+        float* yc = yp + (size_t)co * oplane;
+        *reinterpret_cast<float2*>(yc) = make_float2(v[0][0], v[0][1]);
+        *reinterpret_cast<float2*>(yc + Wo) = make_float2(v[1][0], v[1][1]);
+    }
+}
+
+template <int CIN>
+static int launch_mid5(const float* x, const float* w, const float* bias, float* y, int B, int Cout, int H, int W, int relu,
+                       cudaStream_t s) {
+    MidConv5Params<CIN> p{x, w, bias, y, B, H, W, relu, Cout};
+    const long long z = (long long)B * (Cout / 16);
+    if (z > 65535) return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_mid5: B*Cout/16 too large");
+    dim3 grid((W / 4 + 31) / 32, (H / 4 + 3) / 4, (unsigned)z);
+    midconv5s2_kernel<CIN><<<grid, 128, 0, s>>>(p);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("conv2d_mid5 launch");
+    return MVSTER_OK;
+}
+
 template <int CIN, int COUT>
 static int launch_conv5(const float* x, const float* w_host, const float* bias_host, float* y, int B, int H, int W,
                         int relu, int co_total, int co_off, cudaStream_t s) {
@@ -349,6 +558,68 @@ extern "C" int mvster_conv3d_small(const float* x, const float* w_host, const fl
     SC_CASE(1, 16, 8, 2)   // reg2d.conv11 (unfused form of mvster_regtail's first half)
 #undef SC_CASE
     return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small: no kernel for Cin=%d Cout=%d kd=%d mode=%d", Cin, Cout, kd, mode);
+}
+
+// One slice of `Cout` output channels (co_off .. co_off+Cout-1 of a Cout_total-channel y) of a strided / transposed
+// reg2d layer whose whole filter bank exceeds the kernel-parameter space (conv5: 32->64 stride 2, conv7: 64->32
+// transposed + skip); w_host [1,3,3,Cin,Cout] and bias_host [Cout] hold the slice.
+extern "C" int mvster_conv3d_small_slice(const float* x, const float* w_host, const float* bias_host, const float* skip,
+                                         float* y, int B, int Cin, int Cout, int Cout_total, int co_off, int D, int H,
+                                         int W, int mode, int relu, void* stream) {
+    if (!x || !w_host || !bias_host || !y) return fail(MVSTER_ERR_BAD_ARG, "conv3d_small_slice: null pointer");
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cout <= 0 || co_off < 0 || co_off + Cout > Cout_total)
+        return fail(MVSTER_ERR_BAD_ARG, "conv3d_small_slice: bad dimension / channel slice");
+    if (mode != 1 && mode != 2) return fail(MVSTER_ERR_BAD_ARG, "conv3d_small_slice: mode %d not in {1,2}", mode);
+    if (skip != nullptr && mode != 2) return fail(MVSTER_ERR_BAD_ARG, "conv3d_small_slice: skip is only defined for mode 2");
+    if (mode == 1 && ((H & 1) || (W & 3)))
+        return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small_slice: stride-2 needs H%%2==0, W%%4==0");
+    if ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)skip)) % 16)
+        return fail(MVSTER_ERR_ALIGN, "conv3d_small_slice: tensors must be 16-byte aligned");
+    DeviceGuard guard(y);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Cin == 32 && Cout == 16 && mode == 1)  // reg2d.conv5
+        return launch_small<1, 32, 16, 1>(x, w_host, bias_host, skip, y, B, D, H, W, relu, s, Cout_total, co_off);
+    if (Cin == 64 && Cout == 8 && mode == 2)   // reg2d.conv7 (+ conv4 skip)
+        return launch_small<1, 64, 8, 2>(x, w_host, bias_host, skip, y, B, D, H, W, relu, s, Cout_total, co_off);
+    return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_small_slice: no kernel for Cin=%d Cout=%d mode=%d", Cin, Cout, mode);
+}
+
+// 32/64-channel stride-1 layers with the folded weights in device memory (see midconv_s1_kernel).
+extern "C" int mvster_conv3d_mid(const float* x, const float* w_dev, const float* bias_dev, float* y, int B, int Cin,
+                                 int Cout, int D, int H, int W, int kd, int relu, void* stream) {
+    if (!x || !w_dev || !bias_dev || !y) return fail(MVSTER_ERR_BAD_ARG, "conv3d_mid: null pointer");
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(MVSTER_ERR_BAD_ARG, "conv3d_mid: non-positive dimension");
+    if ((H & 1) || (W & 1)) return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_mid: needs even H, W");
+    if (Cout % 16) return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_mid: Cout=%d is not a multiple of 16", Cout);
+    if ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)w_dev)) % 16)
+        return fail(MVSTER_ERR_ALIGN, "conv3d_mid: tensors must be 16-byte aligned");
+    DeviceGuard guard(y);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (kd == 1 && Cin == 32) return launch_mid<1, 32>(x, w_dev, bias_dev, y, B, Cout, D, H, W, relu, s);
+    if (kd == 1 && Cin == 64) return launch_mid<1, 64>(x, w_dev, bias_dev, y, B, Cout, D, H, W, relu, s);
+    if (kd == 3 && Cin == 32) return launch_mid<3, 32>(x, w_dev, bias_dev, y, B, Cout, D, H, W, relu, s);
+    if (kd == 3 && Cin == 64) return launch_mid<3, 64>(x, w_dev, bias_dev, y, B, Cout, D, H, W, relu, s);
+    return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_mid: no kernel for Cin=%d kd=%d", Cin, kd);
+}
+
+// 5x5 stride-2 padding-2 layers of FPN4 with the folded weights in device memory (see midconv5s2_kernel).
+extern "C" int mvster_conv2d_mid5(const float* x, const float* w_dev, const float* bias_dev, float* y, int B, int Cin,
+                                  int Cout, int H, int W, int relu, void* stream) {
+    if (!x || !w_dev || !bias_dev || !y) return fail(MVSTER_ERR_BAD_ARG, "conv2d_mid5: null pointer");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(MVSTER_ERR_BAD_ARG, "conv2d_mid5: non-positive dimension");
+    if ((H & 3) || (W & 3)) return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_mid5: needs H%%4==0, W%%4==0");
+    if (Cout % 16) return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_mid5: Cout=%d is not a multiple of 16", Cout);
+    if ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)w_dev)) % 16)
+        return fail(MVSTER_ERR_ALIGN, "conv2d_mid5: tensors must be 16-byte aligned");
+    DeviceGuard guard(y);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Cin == 8) return launch_mid5<8>(x, w_dev, bias_dev, y, B, Cout, H, W, relu, s);
+    if (Cin == 16) return launch_mid5<16>(x, w_dev, bias_dev, y, B, Cout, H, W, relu, s);
+    if (Cin == 32) return launch_mid5<32>(x, w_dev, bias_dev, y, B, Cout, H, W, relu, s);
+    return fail(MVSTER_ERR_UNSUPPORTED, "conv2d_mid5: no kernel for Cin=%d", Cin);
 }
 
 // 2-D layers of FPN4 (models/mvs4net_utils.py:431-449, eval mode, BatchNorm folded): NCHW planar fp32 in and out.

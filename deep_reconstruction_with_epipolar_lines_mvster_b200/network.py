@@ -108,10 +108,30 @@ class FPN4(nn.Module):
 
     def _block(self, blk: "Conv2d", tag: str, x):
         k, s = blk.conv.kernel_size[0], blk.conv.stride[0]
+        if k == 5 and s == 2 and ops.conv2d_mid5_supported(blk.conv.in_channels, blk.conv.out_channels, x.shape[2], x.shape[3]):
+            w, b = self._folded_dev(blk, tag, x.device)
+            return ops.conv2d_mid5(x, w[0], b)
         if ops.conv2d_small_supported(blk.conv.in_channels, blk.conv.out_channels, k, s, x.shape[2], x.shape[3]):
             w, b = self._folded(blk, tag)
             return ops.conv2d_small(x, w, b, k, s, True)
+        if k == 3 and s == 1 and ops.conv3d_mid_supported(blk.conv.in_channels, blk.conv.out_channels, 1, x.shape[2], x.shape[3]):
+            w, b = self._folded_dev(blk, tag, x.device)
+            return ops.conv3d_mid(x.unsqueeze(2), w, b).squeeze(2)
         return blk(x)
+
+    def _folded_dev(self, blk: "Conv2d", tag: str, device):
+        """BatchNorm-folded weight ``[1,3,3,ci,co]`` + bias of a Conv2d block, resident on ``device`` (cached)."""
+        conv, bn = blk.conv, blk.bn
+        key = tuple(t._version for t in (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)) \
+            + (conv.weight.data_ptr(), str(device))
+        hit = self._fold_cache.get(tag + "@dev")
+        if hit is None or hit[0] != key:
+            scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+            shift = (bn.bias.detach().double() - bn.running_mean.detach().double() * scale).float()
+            w = (conv.weight.detach().double() * scale.view(-1, 1, 1, 1)).permute(2, 3, 1, 0).float()  # [ky,kx,ci,co]
+            hit = (key, w.unsqueeze(0).contiguous().to(device), shift.contiguous().to(device))
+            self._fold_cache[tag + "@dev"] = hit
+        return hit[1], hit[2]
 
     def forward_direct(self, x) -> Dict[str, torch.Tensor]:
         """Eval-mode FPN4 on the B200 kernels: encoder levels 0-2 as direct convolutions (BatchNorm folded), level 3
@@ -125,7 +145,9 @@ class FPN4(nn.Module):
         c2 = c1
         for i, blk in enumerate(self.conv2):
             c2 = self._block(blk, "c2%d" % i, c2)
-        top = self.conv3(c2)
+        top = c2
+        for i, blk in enumerate(self.conv3):
+            top = self._block(blk, "c3%d" % i, top)
         out = {"stage1": self.out1(top).contiguous(memory_format=torch.channels_last)}
         intra2 = self._up(top) + self.inner1(c2)
         out["stage2"] = self.out2(intra2).contiguous(memory_format=torch.channels_last)
@@ -267,18 +289,39 @@ class reg2d(nn.Module):
         if self.direct_convs and ops.conv3d_small_supported(cin, cout, conv.kernel_size[0], mode, x.shape[3], x.shape[4]):
             w, bias = self._fold_block(name)
             return ops.conv3d_small(x, w, bias, mode, True, skip)
+        if self.direct_convs and ops.conv3d_sliced_supported(cin, cout, conv.kernel_size[0], mode, x.shape[3], x.shape[4]):
+            w, bias = self._fold_block(name)
+            hit = self._fold_cache.get(name + "@slices")
+            if hit is None or hit[0] is not w:
+                cs = ops._CONV3D_SLICE[(cin, cout, mode)]
+                hit = (w, [w[..., i * cs:(i + 1) * cs].contiguous() for i in range(cout // cs)],
+                       [bias[i * cs:(i + 1) * cs].contiguous() for i in range(cout // cs)])
+                self._fold_cache[name + "@slices"] = hit
+            return ops.conv3d_sliced(x, hit[1], hit[2], mode, True, skip)
+        if self.direct_convs and mode == ops.CONV_STRIDE1 and skip is None \
+                and ops.conv3d_mid_supported(cin, cout, conv.kernel_size[0], x.shape[3], x.shape[4]):
+            w, bias = self._fold_block(name)
+            return ops.conv3d_mid(x, *self._on_device(name, w, bias, x.device))
         y = blk(x)
         return y if skip is None else skip + y
 
+    def _on_device(self, name: str, w: torch.Tensor, bias: torch.Tensor, device):
+        """Device copies of a folded filter bank (cached until the fold itself is refreshed)."""
+        hit = self._fold_cache.get(name + "@dev")
+        if hit is None or hit[0] is not w or hit[1].device != device:
+            hit = (w, w.to(device), bias.to(device))
+            self._fold_cache[name + "@dev"] = hit
+        return hit[1], hit[2]
+
     def _trunk_eval(self, x):
-        """``_trunk`` in eval mode: the layers at full / half resolution (conv0-conv3, conv9) run as hand-written
-        direct convolutions with BatchNorm folded and ReLU / skip add fused; the 32- and 64-channel layers at 1/4 and
-        1/8 resolution (conv4-conv7) stay on cuDNN."""
+        """``_trunk`` in eval mode on hand-written direct convolutions with BatchNorm folded and ReLU / skip add fused:
+        conv0-conv3, conv9 with the filter bank in the kernel-parameter space, conv5 / conv7 as one launch per filter-bank
+        slice, conv4 / conv6 (110 / 442 KB of weights) with device-resident weights; cuDNN only where a shape is odd."""
         conv0 = self._direct("conv0", x, ops.CONV_STRIDE1)
         conv2 = self._direct("conv2", self._direct("conv1", conv0, ops.CONV_STRIDE2), ops.CONV_STRIDE1)
-        conv4 = self.conv4(self._direct("conv3", conv2, ops.CONV_STRIDE2))
-        y = self.conv6(self.conv5(conv4))
-        y = conv4 + self.conv7(y)
+        conv4 = self._direct("conv4", self._direct("conv3", conv2, ops.CONV_STRIDE2), ops.CONV_STRIDE1)
+        y = self._direct("conv6", self._direct("conv5", conv4, ops.CONV_STRIDE2), ops.CONV_STRIDE1)
+        y = self._direct("conv7", y, ops.CONV_TRANSPOSED2, skip=conv4)
         return conv0, self._direct("conv9", y, ops.CONV_TRANSPOSED2, skip=conv2)
 
     def forward_direct(self, x):

@@ -294,6 +294,83 @@ def conv3d_small(x: torch.Tensor, w_host: torch.Tensor, bias_host: torch.Tensor,
     return y
 
 
+_CONV3D_SLICE = {(32, 64, CONV_STRIDE2): 16, (64, 32, CONV_TRANSPOSED2): 8}  # (Cin, Cout_total, mode) -> Cout per launch
+
+
+def conv3d_sliced_supported(cin: int, cout: int, kd: int, mode: int, h: int, w: int) -> bool:
+    if kd != 1 or (cin, cout, mode) not in _CONV3D_SLICE:
+        return False
+    return mode == CONV_TRANSPOSED2 or (h % 2 == 0 and w % 4 == 0)
+
+
+def conv3d_sliced(x: torch.Tensor, w_slices, bias_slices, mode: int, relu: bool = True,
+                  skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """reg2d.conv5 / conv7 as one launch per filter-bank slice (``mvster_conv3d_small_slice``).  ``w_slices`` /
+    ``bias_slices``: per-slice contiguous CPU fp32 tensors ``[1,3,3,Cin,cs]`` / ``[cs]``."""
+    x = _f32c(x, "x")
+    b, cin, d, h, w = x.shape
+    cs = w_slices[0].shape[-1]
+    cout = cs * len(w_slices)
+    oh, ow = (h // 2, w // 2) if mode == CONV_STRIDE2 else (2 * h, 2 * w)
+    y = torch.empty((b, cout, d, oh, ow), device=x.device, dtype=torch.float32)
+    if skip is not None:
+        skip = _f32c(skip, "skip")
+        if skip.shape != y.shape:
+            raise RuntimeError("conv3d_sliced: skip %s does not match the output %s" % (tuple(skip.shape), tuple(y.shape)))
+    lib = _lib.load()
+    for i, (ws, bs) in enumerate(zip(w_slices, bias_slices)):
+        if ws.device.type != "cpu" or not ws.is_contiguous() or ws.dtype != torch.float32 or ws.shape[3] != cin:
+            raise RuntimeError("conv3d_sliced: weight slices must be contiguous CPU fp32 [1,3,3,Cin,cs]")
+        _lib.check(lib.mvster_conv3d_small_slice(
+            _ptr(x), ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(bs.data_ptr()), _ptr(skip), _ptr(y), b, cin, cs, cout,
+            i * cs, d, h, w, int(mode), int(bool(relu)), _stream(x)))
+    return y
+
+
+def conv2d_mid5_supported(cin: int, cout: int, h: int, w: int) -> bool:
+    return cin in (8, 16, 32) and cout % 16 == 0 and h % 4 == 0 and w % 4 == 0
+
+
+def conv2d_mid5(x: torch.Tensor, w_dev: torch.Tensor, bias_dev: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """5x5 stride-2 convolution of FPN4's down-sampling layers, folded weights ``[5,5,Cin,Cout]`` resident on the device."""
+    x = _f32c(x, "x")
+    _require_cuda(w_dev, "w_dev")
+    _require_cuda(bias_dev, "bias_dev")
+    b, cin, h, w = x.shape
+    if w_dev.dim() != 4 or tuple(w_dev.shape[:3]) != (5, 5, cin) or not w_dev.is_contiguous() or w_dev.dtype != torch.float32 \
+            or bias_dev.numel() != w_dev.shape[3] or bias_dev.dtype != torch.float32:
+        raise RuntimeError("conv2d_mid5: w_dev must be contiguous fp32 [5,5,Cin,Cout] and bias_dev [Cout]")
+    cout = w_dev.shape[3]
+    y = torch.empty((b, cout, h // 2, w // 2), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_conv2d_mid5(_ptr(x), _ptr(w_dev), _ptr(bias_dev), _ptr(y), b, cin, cout, h, w,
+                                              int(bool(relu)), _stream(x)))
+    return y
+
+
+def conv3d_mid_supported(cin: int, cout: int, kd: int, h: int, w: int) -> bool:
+    """True when ``mvster_conv3d_mid`` has a kernel for this stride-1 layer at input size ``h x w``."""
+    return cin in (32, 64) and cout % 16 == 0 and kd in (1, 3) and h % 2 == 0 and w % 2 == 0
+
+
+def conv3d_mid(x: torch.Tensor, w_dev: torch.Tensor, bias_dev: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """Direct fp32 stride-1 convolution of a 32/64-channel NCDHW volume with folded weights resident on the device
+    (reg2d conv4 / conv6, FPN4 conv3.1 / conv3.2 with D = 1).  ``w_dev`` [kd,3,3,Cin,Cout], ``bias_dev`` [Cout]."""
+    x = _f32c(x, "x")
+    _require_cuda(w_dev, "w_dev")
+    _require_cuda(bias_dev, "bias_dev")
+    if x.dim() != 5 or w_dev.dim() != 5 or not w_dev.is_contiguous() or w_dev.dtype != torch.float32 \
+            or bias_dev.dtype != torch.float32 or not bias_dev.is_contiguous():
+        raise RuntimeError("conv3d_mid: x must be [B,Cin,D,H,W]; w_dev [kd,3,3,Cin,Cout] / bias_dev [Cout] contiguous fp32")
+    b, cin, d, h, w = x.shape
+    kd, _, _, wci, cout = w_dev.shape
+    if wci != cin or bias_dev.numel() != cout:
+        raise RuntimeError("conv3d_mid: weight %s does not match input channels %d" % (tuple(w_dev.shape), cin))
+    y = torch.empty((b, cout, d, h, w), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_conv3d_mid(_ptr(x), _ptr(w_dev), _ptr(bias_dev), _ptr(y), b, cin, cout, d, h, w, int(kd),
+                                             int(bool(relu)), _stream(x)))
+    return y
+
+
 _CONV2D_SLICE = {(3, 3): 8, (8, 3): 8, (16, 3): 16, (32, 3): 16, (8, 5): 16, (16, 5): 16}  # (Cin, k) -> Cout per launch
 
 

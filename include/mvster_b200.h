@@ -156,6 +156,30 @@ int mvster_regtail(const float* low, const float* skip, const float* w, const fl
  */
 int mvster_conv3d_small(const float* x, const float* w, const float* bias, const float* skip, float* y, int B, int Cin,
                         int Cout, int D, int H, int W, int kd, int mode, int relu, void* stream);
+/* 5x5 stride-2 padding-2 Conv2d + BatchNorm + ReLU of FPN4 (conv1.0 / conv2.0 / conv3.0, models/mvs4net_utils.py:438,444,
+ * 446) with the folded weights in DEVICE memory: x dev [B,Cin,H,W], w_dev dev [5,5,Cin,Cout], bias_dev dev [Cout],
+ * y dev [B,Cout,H/2,W/2]; Cin in {8,16,32}, Cout % 16 == 0, H % 4 == 0, W % 4 == 0. */
+int mvster_conv2d_mid5(const float* x, const float* w_dev, const float* bias_dev, float* y, int B, int Cin, int Cout, int H,
+                       int W, int relu, void* stream);
+
+/* One slice of `Cout` output channels of a strided (mode 1) / transposed (mode 2, optional skip) reg2d layer whose filter
+ * bank exceeds the kernel-parameter space: reg2d.conv5 (32->64, slices of 16) and conv7 (64->32, slices of 8),
+ * models/mvs4net_utils.py:899,903.  w_host HOST [1,3,3,Cin,Cout], bias_host HOST [Cout] hold the slice; y (and skip) are
+ * the full Cout_total-channel tensors, the slice writes channels co_off .. co_off+Cout-1. */
+int mvster_conv3d_small_slice(const float* x, const float* w_host, const float* bias_host, const float* skip, float* y,
+                              int B, int Cin, int Cout, int Cout_total, int co_off, int D, int H, int W, int mode,
+                              int relu, void* stream);
+
+/* ---- 32/64-channel stride-1 layers of reg2d / FPN4 with the folded weights in DEVICE memory ----
+ * Replaces, in eval mode, reg2d.conv4 / conv6 (ConvBnReLU3D (3,3,3), models/mvs4net_utils.py:897,901) and FPN4
+ * conv3.1 / conv3.2 (Conv2d 3x3 + BatchNorm + ReLU, :447-448; pass D = 1, kd = 1) - filter banks of 110 .. 442 KB that do
+ * not fit the kernel-parameter space.  BatchNorm is folded by the caller: y = relu(conv(x, w) + bias).
+ *   x dev [B, Cin, D, H, W] fp32;  w_dev dev [kd, 3, 3, Cin, Cout];  bias_dev dev [Cout];  y dev [B, Cout, D, H, W]
+ *   Cin in {32, 64}, Cout % 16 == 0, kd in {1, 3}, H and W even; stride 1, padding (kd/2, 1, 1).
+ */
+int mvster_conv3d_mid(const float* x, const float* w_dev, const float* bias_dev, float* y, int B, int Cin, int Cout,
+                      int D, int H, int W, int kd, int relu, void* stream);
+
 /* ---- FPN4: few-channel 2-D convolutions and the fused top-down step ----------------------
  * mvster_conv2d_small: Conv2d + BatchNorm2d (folded) + ReLU blocks of FPN4's encoder (models/mvs4net_utils.py:431-449,
  * building block :231-258), NCHW planar fp32.  3x3 stride 1 padding 1 (H, W even) or 5x5 stride 2 padding 2 (H even,

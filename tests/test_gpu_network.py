@@ -190,6 +190,88 @@ def test_conv3d_small_matches_float64_torch(cin, cout, kd, mode, d, h, w):
     assert (got.cpu().double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("cin,cout,kd,d,h,w", [(32, 32, 3, 4, 10, 12), (64, 64, 3, 4, 6, 66), (64, 64, 1, 1, 8, 10),
+                                               (32, 32, 3, 1, 4, 4), (64, 64, 3, 8, 2, 2), (32, 64, 1, 2, 12, 70)])
+def test_conv3d_mid_matches_float64_torch(cin, cout, kd, d, h, w):
+    """The 32/64-channel stride-1 kernel (device-resident weights; reg2d conv4 / conv6, FPN4 conv3.1 / conv3.2) against
+    torch's convolution in float64: borders, depth padding of the (3,3,3) kernels, every 16-channel slice."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(cin + cout + kd + h)
+    b = 2
+    x = rng.normal(0, 1, (b, cin, d, h, w)).astype(np.float32)
+    wt = rng.normal(0, 0.1, (kd, 3, 3, cin, cout)).astype(np.float32)
+    bias = rng.normal(0, 0.3, cout).astype(np.float32)
+    ref = F.conv3d(torch.from_numpy(x).double(), torch.from_numpy(wt).double().permute(4, 3, 0, 1, 2), padding=(kd // 2, 1, 1))
+    ref = torch.relu(ref + torch.from_numpy(bias).double().view(1, -1, 1, 1, 1))
+    got = ops.conv3d_mid(torch.from_numpy(x).to(DEV), torch.from_numpy(wt).to(DEV), torch.from_numpy(bias).to(DEV))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert (got.cpu().double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    with pytest.raises(RuntimeError, match="even"):
+        ops.conv3d_mid(torch.zeros((1, cin, 1, 5, 8), device=DEV), torch.from_numpy(wt).to(DEV), torch.from_numpy(bias).to(DEV))
+    with pytest.raises(RuntimeError, match="no kernel|multiple"):
+        ops.conv3d_mid(torch.zeros((1, 16, 1, 4, 8), device=DEV), torch.zeros((1, 3, 3, 16, 24), device=DEV),
+                       torch.zeros(24, device=DEV))
+
+
+@pytest.mark.parametrize("cin,cout,mode,d,h,w", [(32, 64, 1, 4, 12, 72), (32, 64, 1, 1, 2, 4), (64, 32, 2, 4, 5, 7),
+                                                 (64, 32, 2, 8, 1, 33)])
+def test_conv3d_sliced_matches_float64_torch(cin, cout, mode, d, h, w):
+    """reg2d.conv5 (32->64, stride 2) and conv7 (64->32 transposed + skip) as one launch per filter-bank slice."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(cin + cout + h)
+    x = rng.normal(0, 1, (2, cin, d, h, w)).astype(np.float32)
+    wt = rng.normal(0, 0.1, (1, 3, 3, cin, cout)).astype(np.float32)
+    bias = rng.normal(0, 0.3, cout).astype(np.float32)
+    xd, wd = torch.from_numpy(x).double(), torch.from_numpy(wt).double()
+    skip = None
+    if mode == 1:
+        ref = F.conv3d(xd, wd.permute(4, 3, 0, 1, 2), stride=(1, 2, 2), padding=(0, 1, 1))
+    else:
+        ref = F.conv_transpose3d(xd, wd.permute(3, 4, 0, 1, 2), stride=(1, 2, 2), padding=(0, 1, 1), output_padding=(0, 1, 1))
+        skip = rng.normal(0, 1, tuple(ref.shape)).astype(np.float32)
+    ref = torch.relu(ref + torch.from_numpy(bias).double().view(1, -1, 1, 1, 1))
+    if skip is not None:
+        ref = ref + torch.from_numpy(skip).double()
+    cs = ops._CONV3D_SLICE[(cin, cout, mode)]
+    w_t, b_t = torch.from_numpy(wt), torch.from_numpy(bias)
+    got = ops.conv3d_sliced(torch.from_numpy(x).to(DEV), [w_t[..., i * cs:(i + 1) * cs].contiguous() for i in range(cout // cs)],
+                            [b_t[i * cs:(i + 1) * cs].contiguous() for i in range(cout // cs)], mode, True,
+                            None if skip is None else torch.from_numpy(skip).to(DEV))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert (got.cpu().double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_eval_forward_runs_no_cudnn_convolution_for_the_regulariser(model):
+    """In eval mode every reg2d layer of the shipped configuration has a hand-written kernel (cuDNN only for odd shapes)."""
+    r = model.reg[3]
+    x = torch.randn((1, 4, 4, 64, 128), device=DEV)
+    called = []
+    hooks = [m.register_forward_hook(lambda mod, i, o: called.append(type(mod).__name__))
+             for m in r.modules() if isinstance(m, (torch.nn.Conv3d, torch.nn.ConvTranspose3d)) and m is not r.prob]
+    with torch.no_grad():
+        r.forward_fused_tail(x, torch.rand((1, 4, 64, 128), device=DEV) * 400 + 450, 1.0)
+    for h in hooks:
+        h.remove()
+    assert called == [], called
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(8, 16, 16, 24), (16, 32, 8, 132), (32, 64, 12, 8), (32, 64, 4, 4)])
+def test_conv2d_mid5_matches_float64_torch(cin, cout, h, w):
+    """FPN4's 5x5 stride-2 layers (conv1.0 / conv2.0 / conv3.0) on the device-resident-weights kernel."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(cin + cout + w)
+    x = rng.normal(0, 1, (3, cin, h, w)).astype(np.float32)
+    wt = rng.normal(0, 0.1, (5, 5, cin, cout)).astype(np.float32)
+    bias = rng.normal(0, 0.3, cout).astype(np.float32)
+    ref = F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(wt).double().permute(3, 2, 0, 1), stride=2, padding=2)
+    ref = torch.relu(ref + torch.from_numpy(bias).double().view(1, -1, 1, 1))
+    got = ops.conv2d_mid5(torch.from_numpy(x).to(DEV), torch.from_numpy(wt).to(DEV), torch.from_numpy(bias).to(DEV))
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert (got.cpu().double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    with pytest.raises(RuntimeError, match="H%4"):
+        ops.conv2d_mid5(torch.zeros((1, cin, 6, 8), device=DEV), torch.from_numpy(wt).to(DEV), torch.from_numpy(bias).to(DEV))
+
+
 def test_conv3d_small_rejects_unsupported_layers():
     x = torch.zeros((1, 5, 4, 8, 8), device=DEV)
     with pytest.raises(RuntimeError, match="no kernel"):
