@@ -150,7 +150,17 @@ class FPN4(nn.Module):
             top = self._block(blk, "c3%d" % i, top)
         out = {"stage1": self.out1(top).contiguous(memory_format=torch.channels_last)}
         intra2 = self._up(top) + self.inner1(c2)
-        out["stage2"] = self.out2(intra2).contiguous(memory_format=torch.channels_last)
+        if ops.conv3d_mid_supported(self.out2.in_channels, self.out2.out_channels, 1, intra2.shape[2], intra2.shape[3]):
+            key = (self.out2.weight._version, self.out2.weight.data_ptr(), str(x.device))
+            hit = self._fold_cache.get("out2@dev")
+            if hit is None or hit[0] != key:   # plain 3x3 convolution, no BatchNorm / bias / ReLU (mvs4net_utils.py:468)
+                w2 = self.out2.weight.detach().float().permute(2, 3, 1, 0).unsqueeze(0).contiguous().to(x.device)
+                hit = (key, w2, torch.zeros(self.out2.out_channels, device=x.device))
+                self._fold_cache["out2@dev"] = hit
+            feat2 = ops.conv3d_mid(intra2.contiguous().unsqueeze(2), hit[1], hit[2], relu=False).squeeze(2)
+        else:
+            feat2 = self.out2(intra2)
+        out["stage2"] = feat2.contiguous(memory_format=torch.channels_last)
         w3, wi3, bi3 = self._topdown_weights(self.out3, self.inner2, "td3")
         feat3, intra3 = ops.fpn_topdown(intra2, c1, w3, wi3, bi3, want_intra=True)
         w4, wi4, bi4 = self._topdown_weights(self.out4, self.inner3, "td4")
