@@ -121,10 +121,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? 2 : MVSTER_BWD_MINB)
             const Taps t = make_taps(ax, ay, az, h, hyp[d], p.Hs, p.Ws);
 #pragma unroll
             for (int c = 0; c < CPL; ++c) wv[d][c] = 0.0f;
-#ifndef MVSTER_BWD_UNCOND
-#define MVSTER_BWD_UNCOND 0
-#endif
-            if (MVSTER_BWD_UNCOND || t.any) {  // tap offsets are clamped in-bounds: the loads are always safe
+            if (t.any) {
                 const F8 a = load8<T>(srcp + (size_t)t.o00 * C);
                 const F8 bq = load8<T>(srcp + (size_t)t.o01 * C);
                 const F8 cq = load8<T>(srcp + (size_t)t.o10 * C);

@@ -38,6 +38,27 @@ struct SinkhornParams {
 
 constexpr float kLogTiny = -27.6310211159285482f;  // log(1e-12)
 
+// exp / log of the scaling passes.  MVSTER_SINKHORN_FAST=1: one MUFU each (ex2.approx / lg2.approx on pre-scaled
+// arguments, relative error ~2^-22 plus |x| * 2^-24 from the scaling) instead of the ~8-instruction accurate expf /
+// logf; every exponent here is <= 0 after the max subtraction, so the error is relative to a value <= 1.
+#ifndef MVSTER_SINKHORN_FAST
+#define MVSTER_SINKHORN_FAST 1
+#endif
+__device__ __forceinline__ float sk_exp(float x) {
+#if MVSTER_SINKHORN_FAST
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
+__device__ __forceinline__ float sk_log(float x) {
+#if MVSTER_SINKHORN_FAST
+    return __logf(x);
+#else
+    return logf(x);
+#endif
+}
+
 template <int N>
 __device__ __forceinline__ float lse(const float (&x)[N]) {
     float m = x[0];
@@ -46,8 +67,8 @@ __device__ __forceinline__ float lse(const float (&x)[N]) {
     if (fabsf(m) == INFINITY) m = 0.0f;  // torch.logsumexp: infinite maxima are replaced by 0 before the subtraction
     float s = 0.0f;
 #pragma unroll
-    for (int k = 0; k < N; ++k) s += expf(x[k] - m);
-    return logf(s) + m;
+    for (int k = 0; k < N; ++k) s += sk_exp(x[k] - m);
+    return sk_log(s) + m;
 }
 
 template <int D, bool CONT, int NT>
@@ -135,7 +156,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_kernel(const __grid_constant__ Si
             gu[i] = 0.0f;
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
-                const float tm = expf(K(i, j) + u[i] + v[j]);
+                const float tm = sk_exp(K(i, j) + u[i] + v[j]);
                 const float c = tm * M(i, j);
                 gu[i] += c;
                 gv[j] += c;
@@ -177,7 +198,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_kernel(const __grid_constant__ Si
                 for (int i = 0; i < D; ++i) {
                     gl[i] += gu[i];
 #pragma unroll
-                    for (int j = 0; j < NC; ++j) gv[j] -= gu[i] * expf(K(i, j) + v[j] - lu[i]);
+                    for (int j = 0; j < NC; ++j) gv[j] -= gu[i] * sk_exp(K(i, j) + v[j] - lu[i]);
                 }
                 // v_t = log_mu - LSE_i(K + u_{t-1}),  u_{t-1} = log_nu - Lu_{t-1}  (u_0 = 0)
                 if (t > 0) {
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_kernel(const __grid_constant__ Si
                 for (int i = 0; i < D; ++i) {
                     float g = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < NC; ++j) g -= gv[j] * expf(K(i, j) + up[i] - lv[j]);
+                    for (int j = 0; j < NC; ++j) g -= gv[j] * sk_exp(K(i, j) + up[i] - lv[j]);
                     gu[i] = g;
                 }
 #pragma unroll
