@@ -281,8 +281,10 @@ __global__ void __launch_bounds__(128, 3) conv5s2_kernel(const __grid_constant__
 // Their filter banks (110 .. 442 KB) do not fit the kernel-parameter space, and slicing them into <= 32 KB launches
 // leaves each launch with a fraction of a wave at 1/4 .. 1/8 resolution.  Here the folded weights stay in global memory
 // as [kd][ky][kx][ci][co]: a thread owns 2x2 output pixels x 16 output channels, blockIdx.z enumerates (batch, depth,
-// 16-channel slice) so that ONE launch covers every output channel, and the 16 weights of a (tap, ci) are four
-// CTA-uniform 16-byte loads (one L1 transaction per warp) feeding 64 FFMAs.
+// 16-channel slice) so that ONE launch covers every output channel.  The CTA stages the 9 x CIN x 16 weights of the
+// current depth plane in shared memory (<= 36.9 KB) and reads the 16 weights of a (tap, ci) as four warp-uniform
+// LDS.128 broadcasts feeding 64 FFMAs.  (First version: CTA-uniform LDG.128 straight from L1/L2 - the compiler hoisted
+// 36 loads per input channel to hide their latency, 254 registers, 8 warps per SM, 30 % of FP32 peak.)
 template <int KD, int CIN>
 struct MidConvParams {
     const float* x;
@@ -293,15 +295,16 @@ struct MidConvParams {
 };
 
 template <int KD, int CIN>
-__global__ void __launch_bounds__(128, 2) midconv_s1_kernel(const MidConvParams<KD, CIN> p) {
+__global__ void __launch_bounds__(128, 3) midconv_s1_kernel(const MidConvParams<KD, CIN> p) {
     constexpr int COT = 16;
+    __shared__ float4 wsm[9 * CIN * (COT / 4)];  // [ky][kx][ci][16] of the current kd plane (<= 36.9 KB)
     const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 4 + (threadIdx.x >> 5);
     const int nsl = p.co_total / COT;
     const int sl = blockIdx.z % nsl, bd = blockIdx.z / nsl;
     const int b = bd / p.D, d = bd % p.D;
     const int H = p.H, W = p.W;
-    if (2 * i >= W || 2 * j >= H) return;
-    const int x0 = 2 * i, y0 = 2 * j;
+    const bool active = 2 * i < W && 2 * j < H;  // no early exit: every thread stages weights and meets the barriers
+    const int x0 = min(2 * i, W - 2), y0 = min(2 * j, H - 2);
     const size_t plane = (size_t)H * W;
     float acc[2][2][COT];
 #pragma unroll
@@ -316,11 +319,17 @@ __global__ void __launch_bounds__(128, 2) midconv_s1_kernel(const MidConvParams<
     for (int r = 0; r < 4; ++r) vy[r] = (unsigned)(y0 - 1 + r) < (unsigned)H;
 #pragma unroll 1
     for (int kd = 0; kd < KD; ++kd) {
-        const int dz = d + kd - KD / 2;
+        const int dz = d + kd - KD / 2;  // CTA-uniform
         if ((unsigned)dz >= (unsigned)p.D) continue;
+        if (kd > 0) __syncthreads();  // everyone is done with the previous plane
+        {
+            const float* wk = p.w + ((size_t)kd * 9 * CIN) * p.co_total + sl * COT;
+            for (int idx = threadIdx.x; idx < 9 * CIN * (COT / 4); idx += 128)
+                wsm[idx] = __ldg(reinterpret_cast<const float4*>(wk + (size_t)(idx >> 2) * p.co_total) + (idx & 3));
+        }
+        __syncthreads();
         const float* xp = p.x + (((size_t)b * CIN) * p.D + dz) * plane + (size_t)(y0 - 1) * W + x0;
-        const float* wk = p.w + ((size_t)kd * 9 * CIN) * p.co_total + sl * COT;
-#pragma unroll 1
+#pragma unroll 2
         for (int ci = 0; ci < CIN; ++ci) {
             const float* q = xp + (size_t)ci * p.D * plane;
             float in[4][4];
@@ -337,10 +346,10 @@ __global__ void __launch_bounds__(128, 2) midconv_s1_kernel(const MidConvParams<
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const float4* wq = reinterpret_cast<const float4*>(wk + ((size_t)(ky * 3 + kx) * CIN + ci) * p.co_total);
+                    const float4* wq = wsm + ((ky * 3 + kx) * CIN + ci) * (COT / 4);  // warp-uniform: LDS broadcast
 #pragma unroll
                     for (int k = 0; k < COT / 4; ++k) {
-                        const float4 w4 = __ldg(wq + k);
+                        const float4 w4 = wq[k];
                         const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -354,6 +363,7 @@ __global__ void __launch_bounds__(128, 2) midconv_s1_kernel(const MidConvParams<
                 }
         }
     }
+    if (!active) return;
     float* yp = p.y + (((size_t)b * p.co_total + sl * COT) * p.D + d) * plane + (size_t)y0 * W + x0;
 #pragma unroll
     for (int co = 0; co < COT; ++co) {
@@ -388,8 +398,9 @@ static int launch_mid(const float* x, const float* w, const float* bias, float* 
 // ---- 5x5 stride-2 layers with device-resident weights (FPN4 conv1.0 / conv2.0 / conv3.0) --------------------------------
 // ncu on conv5s2_kernel: with a 25 KB filter bank in the kernel-parameter space the constant cache thrashes (issue
 // 15-35 %).  Same recipe as midconv_s1_kernel instead: weights [ky][kx][ci][co] in global memory read as CTA-uniform
-// 16-byte loads, a thread owns 2x2 output pixels x 16 output channels (1600 FFMAs per input channel for 21 input and
-// 100 weight loads), blockIdx.z enumerates (batch, 16-channel slice).
+// shared-memory broadcasts (staged per chunk of 16 input channels, 25.6 KB), a thread owns 2x2 output pixels x 16
+// output channels (1600 FFMAs per input channel for 21 input and 100 weight loads), blockIdx.z enumerates (batch,
+// 16-channel slice).
 template <int CIN>
 struct MidConv5Params {
     const float* x;
@@ -400,15 +411,17 @@ struct MidConv5Params {
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(128, 2) midconv5s2_kernel(const MidConv5Params<CIN> p) {
+__global__ void __launch_bounds__(128, 3) midconv5s2_kernel(const MidConv5Params<CIN> p) {
     constexpr int COT = 16;
+    constexpr int CC = CIN < 16 ? CIN : 16;  // input channels per staged weight chunk (25 * 16 * 16 floats = 25.6 KB)
+    __shared__ float4 wsm[25 * CC * (COT / 4)];  // [ky][kx][cc][16]
     const int Ho = p.H / 2, Wo = p.W / 2;
     const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 4 + (threadIdx.x >> 5);
     const int nsl = p.co_total / COT;
     const int sl = blockIdx.z % nsl, b = blockIdx.z / nsl;
-    if (2 * i >= Wo || 2 * j >= Ho) return;
+    const bool active = 2 * i < Wo && 2 * j < Ho;  // no early exit: every thread stages weights and meets the barriers
     const int H = p.H, W = p.W;
-    const int xi = 4 * i, yi = 4 * j;  // outputs (2j..2j+1, 2i..2i+1) read input rows yi-2..yi+4, columns xi-2..xi+4
+    const int xi = min(4 * i, W - 4), yi = min(4 * j, H - 4);  // outputs read input rows yi-2..yi+4, columns xi-2..xi+4
     const size_t plane = (size_t)H * W, oplane = (size_t)Ho * Wo;
     float acc[2][2][COT];
 #pragma unroll
@@ -424,37 +437,47 @@ __global__ void __launch_bounds__(128, 2) midconv5s2_kernel(const MidConv5Params
     const float* xp = p.x + ((size_t)b * CIN) * plane + (size_t)(yi - 2) * W + xi;
     const float* wk = p.w + sl * COT;
 #pragma unroll 1
-    for (int ci = 0; ci < CIN; ++ci) {
-        const float* q = xp + (size_t)ci * plane;
-        float in[7][7];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) {
-            const float* qr = q + (size_t)r * W;
-            const float2 l = ldz2(qr - 2, vy[r] && vl);
-            const float4 m = ldz4(qr, vy[r]);
-            in[r][0] = l.x; in[r][1] = l.y; in[r][2] = m.x; in[r][3] = m.y; in[r][4] = m.z; in[r][5] = m.w;
-            in[r][6] = ldz(qr + 4, vy[r] && vr);
+    for (int c0 = 0; c0 < CIN; c0 += CC) {
+        if (c0 > 0) __syncthreads();
+        for (int idx = threadIdx.x; idx < 25 * CC * (COT / 4); idx += 128) {
+            const int tap = (idx >> 2) / CC, cc = (idx >> 2) % CC;
+            wsm[idx] = __ldg(reinterpret_cast<const float4*>(wk + ((size_t)tap * CIN + c0 + cc) * p.co_total) + (idx & 3));
         }
+        __syncthreads();
+#pragma unroll 1
+        for (int cc = 0; cc < CC; ++cc) {
+            const float* q = xp + (size_t)(c0 + cc) * plane;
+            float in[7][7];
 #pragma unroll
-        for (int ky = 0; ky < 5; ++ky)
+            for (int r = 0; r < 7; ++r) {
+                const float* qr = q + (size_t)r * W;
+                const float2 l = ldz2(qr - 2, vy[r] && vl);
+                const float4 m = ldz4(qr, vy[r]);
+                in[r][0] = l.x; in[r][1] = l.y; in[r][2] = m.x; in[r][3] = m.y; in[r][4] = m.z; in[r][5] = m.w;
+                in[r][6] = ldz(qr + 4, vy[r] && vr);
+            }
 #pragma unroll
-            for (int kx = 0; kx < 5; ++kx) {
-                const float4* wq = reinterpret_cast<const float4*>(wk + ((size_t)(ky * 5 + kx) * CIN + ci) * p.co_total);
+            for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
-                for (int k = 0; k < COT / 4; ++k) {
-                    const float4 w4 = __ldg(wq + k);
-                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                for (int kx = 0; kx < 5; ++kx) {
+                    const float4* wq = wsm + ((ky * 5 + kx) * CC + cc) * (COT / 4);  // warp-uniform: LDS broadcast
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int co = 4 * k + e;
-                        acc[0][0][co] = fmaf(wv[e], in[ky][kx], acc[0][0][co]);
-                        acc[0][1][co] = fmaf(wv[e], in[ky][kx + 2], acc[0][1][co]);
-                        acc[1][0][co] = fmaf(wv[e], in[ky + 2][kx], acc[1][0][co]);
-                        acc[1][1][co] = fmaf(wv[e], in[ky + 2][kx + 2], acc[1][1][co]);
+                    for (int k = 0; k < COT / 4; ++k) {
+                        const float4 w4 = wq[k];
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int co = 4 * k + e;
+                            acc[0][0][co] = fmaf(wv[e], in[ky][kx], acc[0][0][co]);
+                            acc[0][1][co] = fmaf(wv[e], in[ky][kx + 2], acc[0][1][co]);
+                            acc[1][0][co] = fmaf(wv[e], in[ky + 2][kx], acc[1][0][co]);
+                            acc[1][1][co] = fmaf(wv[e], in[ky + 2][kx + 2], acc[1][1][co]);
+                        }
                     }
                 }
-            }
+        }
     }
+    if (!active) return;
     float* yp = p.y + ((size_t)b * p.co_total + sl * COT) * oplane + (size_t)(2 * j) * Wo + 2 * i;
 #pragma unroll
     for (int co = 0; co < COT; ++co) {
