@@ -35,8 +35,10 @@ namespace mvster {
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C, int CPG, int D, bool TMA, typename T>
-__global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
-    using S = Split<C, CPG, D>;
+__global__ void __launch_bounds__(Split<C, CPG, D, (int)sizeof(T)>::WARPS * 32, Split<C, CPG, D, (int)sizeof(T)>::MINB)
+    epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
+    using S = Split<C, CPG, D, (int)sizeof(T)>;
+    using Gm = TmaGeom<C, (int)sizeof(T)>;
     constexpr int CH = S::CH, DL = S::DL, LC = S::LC, L = S::L, PPW = S::PPW, GPL = S::GPL, NCHUNK = S::NCHUNK;
     constexpr int G = C / CPG;
     constexpr int WX = S::WX, TILE_H = S::TILE_H;  // CTA tile: 32 x 8 pixels
@@ -46,14 +48,14 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
 
     extern __shared__ unsigned char smem_raw[];
     // TMA variant: [buf0 | buf1] 1024-aligned, then 2 mbarriers + 3 bbox slots; both variants: homographies at the end
-    constexpr int BH = (TILE_H + TmaGeom<C>::BH_EXTRA);
-    constexpr int BUF_BYTES = TMA ? TmaGeom<C>::BW * BH * TB : 0;
-    constexpr int ROW_BYTES = TmaGeom<C>::BW * TB;
+    constexpr int BH = (TILE_H + Gm::BH_EXTRA);
+    constexpr int BUF_BYTES = TMA ? Gm::BW * BH * TB : 0;
+    constexpr int ROW_BYTES = Gm::BW * TB;
     const uint32_t smem_base = TMA ? ((smem_u32(smem_raw) + 1023u) & ~1023u) : smem_u32(smem_raw);
     const uint32_t ctl = smem_base + 2u * BUF_BYTES;
     unsigned char* ctl_ptr = smem_raw + (ctl - smem_u32(smem_raw));
     int* bbox = reinterpret_cast<int*>(ctl_ptr + 16);                                  // [3][4] (TMA only)
-    float* rt_s = reinterpret_cast<float*>(ctl_ptr + (TMA ? TmaGeom<C>::CTL_BYTES : 0));  // [Nsrc][12]
+    float* rt_s = reinterpret_cast<float*>(ctl_ptr + (TMA ? Gm::CTL_BYTES : 0));  // [Nsrc][12]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
     const int cl = lane % LC;         // channel chunk of this lane
     const int dl = (lane % L) / LC;   // hypothesis chunk of this lane
     const int b = blockIdx.z;
-    for (int i = tid; i < p.Nsrc * 12; i += MVSTER_TMA_WARPS * 32) rt_s[i] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + i);
+    for (int i = tid; i < p.Nsrc * 12; i += S::WARPS * 32) rt_s[i] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + i);
     int x = blockIdx.x * S::TILE_W + (warp % WX) * PPW + pix;
     int y = blockIdx.y * TILE_H + (warp / WX);
     const bool live = (x < p.W) && (y < p.H);
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(MVSTER_TMA_WARPS * 32, MVSTER_TMA_MINB) epi_fw
         __syncthreads();  // bbox complete; every thread has also finished gathering from buffer v&1 (view v-2)
         const int4 bb = *reinterpret_cast<const int4*>(&bbox[slot * 4]);
         nbx = bb.x; nby = bb.y;
-        nfit = (bb.z - bb.x + 2 <= TmaGeom<C>::BW) && (bb.w - bb.y + 2 <= BH);  // +1 for the right / bottom tap
+        nfit = (bb.z - bb.x + 2 <= Gm::BW) && (bb.w - bb.y + 2 <= BH);  // +1 for the right / bottom tap
         if (nfit && tid == 0) {
             const uint32_t bar = ctl + 8u * (v & 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
@@ -619,11 +621,12 @@ __global__ void __launch_bounds__(LineGeom::WARPS * 32, MVSTER_LINE_MINB) epi_fw
 // ---------------------------------------------------------------------------------------------------------------------
 template <int C, int CPG, int D, bool TMA, typename T>
 static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
-    using S = Split<C, CPG, D>;
+    using S = Split<C, CPG, D, (int)sizeof(T)>;
+    using Gm = TmaGeom<C, (int)sizeof(T)>;
     constexpr int TILE_H = S::TILE_H;
     constexpr int TB = C * (int)sizeof(T);
     const int smem = MVSTER_MAX_SRC_VIEWS * 48 +
-                     (TMA ? 2 * TmaGeom<C>::BW * (TILE_H + TmaGeom<C>::BH_EXTRA) * TB + 1024 + TmaGeom<C>::CTL_BYTES : 0);
+                     (TMA ? 2 * Gm::BW * (TILE_H + Gm::BH_EXTRA) * TB + 1024 + Gm::CTL_BYTES : 0);
     static bool attr_done[64] = {};
     if (smem > 48 * 1024) {
         const int st = ensure_dynamic_smem(epi_fwd_kernel<C, CPG, D, TMA, T>, smem, attr_done, "epi_fwd: cudaFuncSetAttribute");
@@ -631,7 +634,7 @@ static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
     }
     dim3 grid((p.W + S::TILE_W - 1) / S::TILE_W, (p.H + TILE_H - 1) / TILE_H, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
-    epi_fwd_kernel<C, CPG, D, TMA, T><<<grid, MVSTER_TMA_WARPS * 32, smem, stream>>>(p);
+    epi_fwd_kernel<C, CPG, D, TMA, T><<<grid, S::WARPS * 32, smem, stream>>>(p);
     count_launch();
     MVSTER_CHECK_LAUNCH("epi_fwd launch");
     return MVSTER_OK;

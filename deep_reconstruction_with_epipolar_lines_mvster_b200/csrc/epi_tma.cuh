@@ -29,29 +29,39 @@ namespace mvster {
 // ---------------------------------------------------------------------------------------------------------------------
 // lane decomposition of the TMA-staged kernel: one lane owns all C <= 16 channels and all D hypotheses of a pixel
 // ---------------------------------------------------------------------------------------------------------------------
-template <int C, int CPG, int D>
+// 64-byte texels (C = 16 fp32): the per-sample gather is twice as long as for 32-byte texels, and two lanes per pixel
+// (each owning half of the hypotheses) at 24 warps per SM beat one lane at 16 warps (stage 3: 0.374 -> 0.352 ms); for
+// 32-byte texels the single-lane layout wins (A/B in gpurun_out/variants2.log).  ES = bytes per feature element.
+template <int C, int ES>
+struct WideTexel {
+    static constexpr bool value = (C * ES == 64);
+};
+
+template <int C, int CPG, int D, int ES = 4>
 struct Split {
     static constexpr int CH = C;                           // channels per lane
     static constexpr int GPL = CH / CPG;                   // correlation groups per lane
-    static constexpr int LD = MVSTER_TMA_LD;               // lanes splitting the hypotheses of a pixel
+    static constexpr int LD = (WideTexel<C, ES>::value && D % 2 == 0) ? 2 : MVSTER_TMA_LD;  // lanes splitting the hypotheses
     static constexpr int DL = D / LD;                      // hypotheses per lane
     static constexpr int LC = 1, L = LD;                   // lanes per pixel
     static constexpr int PPW = 32 / L;                     // pixels per warp
     static constexpr int NCHUNK = CH / 8;                  // 8-channel chunks per lane
-    static constexpr int WX = L;                           // warps side by side in x (8 warps per CTA)
-    static constexpr int TILE_W = 32, TILE_H = MVSTER_TMA_WARPS / WX;
+    static constexpr int WX = L;                           // warps side by side in x
+    static constexpr int WARPS = (LD == 2 && MVSTER_TMA_LD == 1) ? 8 : MVSTER_TMA_WARPS;   // warps per CTA
+    static constexpr int MINB = (LD == 2 && MVSTER_TMA_LD == 1) ? 3 : MVSTER_TMA_MINB;     // CTAs per SM
+    static constexpr int TILE_W = 32, TILE_H = WARPS / WX;
     static_assert(CH % 8 == 0 && 8 % CPG == 0, "a lane's 8-channel chunks must hold whole groups");
 };
 
 
-template <int C>
+template <int C, int ES = 4>
 struct TmaGeom {
-    static constexpr int TB = C * 4;  // texel bytes (32 or 64)
+    static constexpr int TB = C * ES;  // texel bytes (16, 32 or 64)
     // staging box in texels; the width is a multiple of 8 so that the swizzle phase depends on x only.  Sized for
     // ~25 % scale change / a dozen texels of epipolar span across a tile; larger footprints take the direct path.
     static constexpr int BW = MVSTER_TMA_BW;
     static constexpr int CTL_BYTES = 16 /* 2 mbarriers */ + 48 /* 3 bbox slots */;
-    static constexpr int BH_EXTRA = MVSTER_TMA_BHX;  // box height = tile height + BH_EXTRA
+    static constexpr int BH_EXTRA = WideTexel<C, ES>::value ? 4 : MVSTER_TMA_BHX;  // box height = tile height + BH_EXTRA
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -171,14 +181,14 @@ static inline EncodeTiledFn get_encode_fn() {
 template <int C, int CPG, int D, typename T>
 static inline bool make_maps(CUtensorMap* tmap, const void* const* src, int Nsrc, int B, int Hs, int Ws) {
     constexpr int ES = (int)sizeof(T), TBY = C * ES;
-    using S = Split<C, CPG, D>;
+    using S = Split<C, CPG, D, ES>;
     constexpr int TILE_H = S::TILE_H;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)TBY, (cuuint64_t)Ws * TBY, (cuuint64_t)Hs * Ws * TBY};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TmaGeom<C>::BW, (cuuint32_t)(TILE_H + TmaGeom<C>::BH_EXTRA), 1};
+    const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TmaGeom<C, ES>::BW, (cuuint32_t)(TILE_H + TmaGeom<C, ES>::BH_EXTRA), 1};
     // the swizzle span equals the texel size: 8 neighbouring texels land in 8 different 16-byte bank groups
     const CUtensorMapSwizzle swz = TBY == 16 ? CU_TENSOR_MAP_SWIZZLE_NONE
                                    : (TBY == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
