@@ -16,36 +16,39 @@ from . import ops
 
 
 class SinkhornLoss(torch.autograd.Function):
-    """stats = SinkhornLoss.apply(gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous, inverse)
+    """stats, T_map = SinkhornLoss.apply(gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous, inverse, want_tmap)
 
     ``stats`` = (mean OT loss over masked pixels, masked-pixel count, range_err_ratio); only ``stats[0]`` is
-    differentiable, and only w.r.t. ``attn_weight`` (``hypo_depth`` is detached upstream, models/MVS4Net.py:116)."""
+    differentiable, and only w.r.t. ``attn_weight`` (``hypo_depth`` is detached upstream, models/MVS4Net.py:116).
+    ``T_map`` is the transport map when ``want_tmap`` (else an empty tensor), never differentiated."""
 
     @staticmethod
-    def forward(ctx, gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous, inverse_depth):
+    def forward(ctx, gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous, inverse_depth, want_tmap=False):
         need = attn_weight.requires_grad
-        stats, grad_px, _ = ops.sinkhorn_fwd(gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous,
-                                             inverse_depth, want_grad=need)
+        stats, grad_px, tmap = ops.sinkhorn_fwd(gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous,
+                                                inverse_depth, want_grad=need, want_tmap=want_tmap)
         if need:
             ctx.save_for_backward(grad_px, stats)
-        return stats
+        if tmap is None:
+            tmap = stats.new_empty(0)
+        ctx.mark_non_differentiable(tmap)
+        return stats, tmap
 
     @staticmethod
-    def backward(ctx, grad_stats):
+    def backward(ctx, grad_stats, _grad_tmap):
         grad_px, stats = ctx.saved_tensors
         grad_attn = ops.sinkhorn_bwd(grad_px, stats, grad_stats.contiguous()[0:1])
-        return None, None, grad_attn, None, None, None, None, None
+        return None, None, grad_attn, None, None, None, None, None, None
 
 
 def sinkhorn(gt_depth, hypo_depth, attn_weight, mask, iters, eps=1, continuous=False):
-    """Reference signature (models/mvs4net_utils.py:1164): returns ``(T_map [B,HW,D,D(+1)], loss)``.
+    """Reference signature (models/mvs4net_utils.py:1164): returns ``(T_map [B,HW,D,D(+1)], loss)`` from ONE launch.
 
     ``T_map`` is returned detached (the reference never differentiates through it: every caller takes ``[1]``,
     models/MVS4Net.py:234,281); ``loss`` carries the gradient to ``attn_weight``."""
-    loss = SinkhornLoss.apply(gt_depth, hypo_depth, attn_weight, mask, int(iters), float(eps), bool(continuous), False)[0]
-    _, _, tmap = ops.sinkhorn_fwd(gt_depth, hypo_depth, attn_weight.detach(), mask, int(iters), float(eps),
-                                  bool(continuous), False, want_grad=False, want_tmap=True)
-    return tmap, loss
+    stats, tmap = SinkhornLoss.apply(gt_depth, hypo_depth, attn_weight, mask, int(iters), float(eps), bool(continuous),
+                                     False, True)
+    return tmap, stats[0]
 
 
 def MVS4net_loss(inputs: Dict[str, dict], depth_gt_ms: Dict[str, torch.Tensor], mask_ms: Dict[str, torch.Tensor],
@@ -72,8 +75,8 @@ def MVS4net_loss(inputs: Dict[str, dict], depth_gt_ms: Dict[str, torch.Tensor], 
             this_l1 = torch.nn.functional.l1_loss(stage_inputs["mono_depth"][mask], depth_gt[mask], reduction="mean")
         else:
             this_l1 = torch.tensor(0.0, dtype=torch.float32, device=dev)
-        stats = SinkhornLoss.apply(depth_gt, stage_inputs["hypo_depth"], stage_inputs["attn_weight"], mask,
-                                   int(ot_iter), float(ot_eps), bool(ot_continous), bool(inverse))
+        stats, _ = SinkhornLoss.apply(depth_gt, stage_inputs["hypo_depth"], stage_inputs["attn_weight"], mask,
+                                      int(ot_iter), float(ot_eps), bool(ot_continous), bool(inverse))
         this_ot = stats[0]
         range_err_ratio.append(stats[2].detach())
         stage_l1_loss.append(this_l1)

@@ -445,7 +445,7 @@ def bench_sinkhorn(args, dev):
     def fused():
         for gt, hypo, attn, mask in stages:
             attn.grad = None
-            L.SinkhornLoss.apply(gt, hypo, attn, mask, 10, 1.0, False, True)[0].backward()
+            L.SinkhornLoss.apply(gt, hypo, attn, mask, 10, 1.0, False, True)[0][0].backward()
 
     def eager():
         for gt, hypo, attn, mask in stages:

@@ -88,7 +88,7 @@ def test_matches_float64_oracle_on_seeded_inputs(d, iters, eps, cont):
     mask = torch.rand(b, h, w, generator=gen) > 0.4
     ref = O.sinkhorn_np(gt.numpy(), hypo.numpy(), attn.numpy(), mask.numpy(), iters, eps, cont, inverse_depth=True)
     a = attn.to(DEV).requires_grad_(True)
-    stats = L.SinkhornLoss.apply(gt.to(DEV), hypo.to(DEV), a, mask.to(DEV), iters, eps, cont, True)
+    stats, _ = L.SinkhornLoss.apply(gt.to(DEV), hypo.to(DEV), a, mask.to(DEV), iters, eps, cont, True)
     stats[0].backward()
     assert abs(float(stats[0]) - ref["loss"]) < 2e-5 * abs(ref["loss"])
     assert int(stats[1]) == ref["count"] and abs(float(stats[2]) - ref["range_err_ratio"]) < 1e-6
