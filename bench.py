@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32", help="feature storage type")
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the host-buffer leg (default min(steps,10))")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
-                    help="issue the 16 launches of a step eagerly instead of replaying them as one CUDA graph")
+                    help="issue the launches of a step eagerly instead of replaying them as one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-network", action="store_true",
                     help="skip the secondary whole-network (FPN4 + reg2d + hot path) measurement on rank 0 at N=1")
@@ -340,7 +340,7 @@ def main():
         plan.run()
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     use_graph = args.graph
-    if use_graph:  # the 16 launches of a step replayed as one CUDA graph
+    if use_graph:  # the launches of a step replayed as one CUDA graph
         try:
             plan.capture()
         except Exception as exc:  # capture is an optimisation: fall back to eager launches and say so in the line

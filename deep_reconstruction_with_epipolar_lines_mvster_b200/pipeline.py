@@ -3,8 +3,8 @@ buffer pre-allocated and every launch issued straight through the C ABI.
 
 Per stage it runs, on one stream and with no host synchronisation:
 
+    homography composition (all stages in ONE launch, up front)        -> rt        [B,N-1,12]
     hypothesis schedule (init_inverse_range / schedule_inverse_range)  -> depth_hypo [B,D,H,W]
-    homography composition                                              -> rt        [B,N-1,12]
     fused warp + correlation + epipolar attention + aggregation (K1)    -> cor_feats [B,G,D,H,W]
     regnet(cor_feats) -> logits            (caller-supplied callable; OUT OF SCOPE of this library - cuDNN in the
                                             reference - so benchmarks pass pre-computed logits)
@@ -47,12 +47,14 @@ class CascadePlan:
         self.features: List[List[torch.Tensor]] = [
             [torch.empty((batch, h, w, c), device=dev, dtype=feature_dtype) for _ in range(nviews)]
             for (h, w), c in zip(self.shapes, self.channels)]
-        self.proj = [torch.zeros((batch, nviews, 2, 4, 4), device=dev, dtype=f32) for _ in range(self.nstage)]
+        self.proj_all = torch.zeros((self.nstage, batch, nviews, 2, 4, 4), device=dev, dtype=f32)  # one compose launch
+        self.proj = [self.proj_all[s] for s in range(self.nstage)]
         self.depth_values = torch.empty((batch, 2), device=dev, dtype=f32)
         self.logits = [torch.zeros((batch, d, h, w), device=dev, dtype=f32)
                        for (h, w), d in zip(self.shapes, self.ndepths)]
         # outputs / intermediates
-        self.rt = [torch.empty((batch, nviews - 1, 12), device=dev, dtype=f32) for _ in range(self.nstage)]
+        self.rt_all = torch.empty((self.nstage, batch, nviews - 1, 12), device=dev, dtype=f32)
+        self.rt = [self.rt_all[s] for s in range(self.nstage)]
         self.hypo = [torch.empty((batch, d, h, w), device=dev, dtype=f32) for (h, w), d in zip(self.shapes, self.ndepths)]
         self.volume = [torch.empty((batch, g, d, h, w), device=dev, dtype=f32)
                        for (h, w), g, d in zip(self.shapes, self.groups, self.ndepths)]
@@ -89,11 +91,12 @@ class CascadePlan:
             if stage_ready is not None:
                 torch.cuda.current_stream(self.device).wait_event(stage_ready[s])
             if s == 0:
+                # every stage's projections arrive before stage 0's features (run_from_host copies them first)
+                check(lib.mvster_compose_homographies(P(self.proj_all), P(self.rt_all), self.nstage * B, N, st))
                 check(lib.mvster_init_inverse_range(P(self.depth_values), 2, P(self.hypo[0]), B, d, h, w, st))
             else:
                 check(lib.mvster_schedule_inverse_range(P(self.inv_min[s - 1]), P(self.inv_max[s - 1]), P(self.hypo[s]),
                                                         B, d, h, w, st))
-            check(lib.mvster_compose_homographies(P(self.proj[s]), P(self.rt[s]), B, N, st))
             timed = time_stage == s and self.stage_events is not None
             if timed:
                 self.stage_events[0].record()
@@ -108,9 +111,12 @@ class CascadePlan:
                                   P(self.inv_max[s]), B, d, h, w, st))
         return self.depth[-1], self.conf[-1]
 
-    LAUNCHES_PER_RUN = 16  # 4 stages x (schedule, compose, K1, tail)
+    # compose (all stages), then per stage: hypothesis schedule, K1, tail.  (Building the hypotheses inside K1 instead
+    # was measured and rejected: the stage-4 K1 kernel is issue-bound, the extra prologue cost 0.10 ms against the
+    # 0.065 ms schedule launch it removed.)
+    LAUNCHES_PER_RUN = 13
 
-    # ---- CUDA graph: the 16 launches of one cascade as a single graph launch --------------------------------------
+    # ---- CUDA graph: the launches of one cascade as a single graph launch --------------------------------------
     def capture(self):
         """Capture ``run()`` into a CUDA graph (all buffers are pre-allocated and the kernels take raw pointers, so
         the captured launches stay valid).  Only possible without a Python ``regnet`` callback."""
@@ -159,8 +165,9 @@ class CascadePlan:
         cs.wait_stream(cur)  # the previous step's kernels are done reading the device buffers
         with torch.cuda.stream(cs):
             self.depth_values.copy_(self.h_depth_values, non_blocking=True)
-            for s in range(self.nstage):
+            for s in range(self.nstage):   # all projections first: stage 0 composes the homographies of every stage
                 self.proj[s].copy_(self.h_proj[s], non_blocking=True)
+            for s in range(self.nstage):
                 for a, b in zip(self.h_features[s], self.features[s]):
                     b.copy_(a, non_blocking=True)
                 self._stage_ready[s].record(cs)

@@ -31,7 +31,7 @@ tot = sum(sum(v) / len(v) for v in agg.values())
 with open(os.path.join(out, "%s_launches.md" % tag), "w") as f:
     f.write("# ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-network --e2e-steps 1` (%s)\n\n" % tag)
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised launches: compare SHARES.\n")
-    f.write("One cascade step = 16 launches of this library (4 stages x schedule/compose/K1/tail).\n\n")
+    f.write("One cascade step = 13 launches of this library: compose (all stages), then 4 stages x schedule/K1/tail.\n\n")
     f.write("| kernel | grid | launches seen | mean µs | share of one step |\n|---|---|---|---|---|\n")
     for (name, grid), v in agg.items():
         m = sum(v) / len(v)
