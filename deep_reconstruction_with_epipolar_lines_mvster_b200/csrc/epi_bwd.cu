@@ -49,8 +49,11 @@ __device__ __forceinline__ void red8(float* p, const float* v) {
 #ifndef MVSTER_BWD_MINB
 #define MVSTER_BWD_MINB 3
 #endif
+#ifndef MVSTER_BWD_MINB8
+#define MVSTER_BWD_MINB8 3  // D = 8 (coarse stages): 168 registers + 16-48 bytes of spills at 12 warps per SM beat 248 registers at 8 (stage 2: 0.182 -> 0.152 ms)
+#endif
 template <int C, int CPG, int D, typename T>
-__global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? 2 : MVSTER_BWD_MINB)
+__global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : MVSTER_BWD_MINB)
     epi_bwd_kernel(const __grid_constant__ EpiBwdParams p) {
     constexpr int CPL = 8;
     constexpr int L = C / CPL;
