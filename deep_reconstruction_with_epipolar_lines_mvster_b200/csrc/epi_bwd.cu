@@ -253,12 +253,14 @@ struct EpiBwdTmaParams {
     EpiBwdParams q;
 };
 
+// CTAs per SM: 32-byte texels run best at 4 (128 registers, ~70 bytes of spills: stage 4 0.226 -> 0.216 ms), 64-byte
+// texels at 3 (at 4: stage 3 0.121 -> 0.129 ms)
 #ifndef MVSTER_BWD_TMA_MINB
-#define MVSTER_BWD_TMA_MINB 3
+#define MVSTER_BWD_TMA_MINB(C) ((C) == 8 ? 4 : 3)
 #endif
 
 template <int C, int CPG, int D>
-__global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB)
+__global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB(C))
     epi_bwd_tma_kernel(const __grid_constant__ EpiBwdTmaParams pp) {
     const EpiBwdParams& p = pp.q;
     constexpr int L = C / 8, PPW = 32 / L, GPL = 8 / CPG, G = C / CPG, NT = 128;

@@ -19,6 +19,9 @@
 
 namespace mvster {
 
+#ifndef MVSTER_MID_MINB
+#define MVSTER_MID_MINB 3  // CTAs per SM of the midconv kernels
+#endif
 constexpr int kScUnroll = 2;  // input channels per loop body (bounded registers; weights come through LDCU)
 
 template <int KD, int CIN, int COUT>
@@ -295,7 +298,7 @@ struct MidConvParams {
 };
 
 template <int KD, int CIN>
-__global__ void __launch_bounds__(128, 3) midconv_s1_kernel(const MidConvParams<KD, CIN> p) {
+__global__ void __launch_bounds__(128, MVSTER_MID_MINB) midconv_s1_kernel(const MidConvParams<KD, CIN> p) {
     constexpr int COT = 16;
     __shared__ float4 wsm[9 * CIN * (COT / 4)];  // [ky][kx][ci][16] of the current kd plane (<= 36.9 KB)
     const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 4 + (threadIdx.x >> 5);
@@ -411,7 +414,7 @@ struct MidConv5Params {
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(128, 3) midconv5s2_kernel(const MidConv5Params<CIN> p) {
+__global__ void __launch_bounds__(128, MVSTER_MID_MINB) midconv5s2_kernel(const MidConv5Params<CIN> p) {
     constexpr int COT = 16;
     constexpr int CC = CIN < 16 ? CIN : 16;  // input channels per staged weight chunk (25 * 16 * 16 floats = 25.6 KB)
     __shared__ float4 wsm[25 * CC * (COT / 4)];  // [ky][kx][cc][16]
