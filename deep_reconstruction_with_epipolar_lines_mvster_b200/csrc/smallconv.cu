@@ -19,6 +19,10 @@
 
 namespace mvster {
 
+#ifndef MVSTER_MID_UNROLL
+#define MVSTER_MID_UNROLL 2  // input channels per loop body of midconv_s1_kernel
+#endif
+constexpr int kMidUnroll = MVSTER_MID_UNROLL;
 #ifndef MVSTER_MID_MINB
 #define MVSTER_MID_MINB 3  // CTAs per SM of the midconv kernels
 #endif
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(128, MVSTER_MID_MINB) midconv_s1_kernel(const 
         }
         __syncthreads();
         const float* xp = p.x + (((size_t)b * CIN) * p.D + dz) * plane + (size_t)(y0 - 1) * W + x0;
-#pragma unroll 2
+#pragma unroll kMidUnroll
         for (int ci = 0; ci < CIN; ++ci) {
             const float* q = xp + (size_t)ci * p.D * plane;
             float in[4][4];
