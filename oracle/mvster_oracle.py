@@ -1,8 +1,9 @@
 """CPU oracle for the MVSTER cost-volume hot path.  TEST INFRASTRUCTURE ONLY.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
-import this file, and only as the checker / the timed CPU baseline.  The product package never imports it and has
-no CPU fallback.
+import this file, and only as the checker / the timed CPU baseline (``scripts/bench_extra.py`` additionally times the
+``*_port`` functions as the "reference op sequence in eager PyTorch" baseline of its secondary benchmarks - again as the
+thing compared against, never as the product).  The product package never imports it and has no CPU fallback.
 
 This is a from-scratch restatement of the reference algorithm (olivier-2018/Deep_reconstruction_with_epipolar_lines_MVSTER);
 every function cites the reference lines it follows.  All ``file:line`` citations are relative to the reference tree.
@@ -11,7 +12,8 @@ Parity status: PINNED.  The reference ships no tests or golden vectors (SURVEY.m
 itself: ``tests/golden/make_golden.py`` imports the unmodified reference (``models.mvs4net_utils`` and, via ``ast``,
 the filter functions of ``test_mvs4.py``) in the build container, runs it on seeded synthetic inputs and freezes
 inputs+outputs as ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function below against
-those files.
+those files; ``tests/golden/make_golden_sinkhorn.py`` / ``make_golden_train.py`` do the same for the OT loss
+(``sinkhorn``, ``MVS4net_loss``) and for one whole training step, checked by ``tests/test_sinkhorn_oracle.py``.
 
 Two flavours are provided for the fused op:
   * ``*_np``   float64 NumPy, per-pixel "exact" math (Appendix A of SURVEY.md) - the numerical ground truth;
