@@ -197,14 +197,15 @@ __global__ void __launch_bounds__(Split<C, CPG, D, (int)sizeof(T)>::WARPS * 32, 
                     const float fx = sx[d] - x0f, fy = sy[d] - y0f;
                     const int rx = x0i - bx, ry = y0i - by;
                     if (d == 0 || rx != prx || ry != pry) {
-                        const uint32_t xo = (uint32_t)rx * TB;
-                        const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + xo;
-                        const uint32_t mA = (xo >> 3) & SWZ, mB = ((xo + TB) >> 3) & SWZ;
-                        const uint32_t aL = base ^ mA, aR = (base + TB) ^ mB;
-                        lds_chunk8<T>(aL, t00);
-                        lds_chunk8<T>(aR, t01);
-                        lds_chunk8<T>(aL + ROW_BYTES, t10);
-                        lds_chunk8<T>(aR + ROW_BYTES, t11);
+                        // the swizzle bits come from the x offset only (buffer and rows are multiples of 512 bytes), so
+                        // they can be taken from the address itself; the lower row is an immediate offset
+                        static_assert(SWZ == 0 || (ROW_BYTES % 512 == 0 && BUF_BYTES % 512 == 0), "swizzle phase must depend on x only");
+                        const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + (uint32_t)rx * TB, baseR = base + TB;
+                        const uint32_t aL = base ^ ((base >> 3) & SWZ), aR = baseR ^ ((baseR >> 3) & SWZ);
+                        lds_chunk8_at<T, 0>(aL, t00);
+                        lds_chunk8_at<T, 0>(aR, t01);
+                        lds_chunk8_at<T, ROW_BYTES>(aL, t10);
+                        lds_chunk8_at<T, ROW_BYTES>(aR, t11);
                     }
                     prx = rx; pry = ry;
                     const float gx = 1.0f - fx, gy = 1.0f - fy;

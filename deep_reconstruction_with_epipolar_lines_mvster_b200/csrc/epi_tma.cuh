@@ -155,6 +155,23 @@ __device__ __forceinline__ void lds_chunk8(uint32_t a, P8& t) {
     }
 }
 
+// Same with a compile-time byte offset folded into the load instructions ([reg + imm]): the XOR that finds the second
+// half is computed once per texel column and shared by both rows.
+template <int OFF>
+__device__ __forceinline__ void lds_pairs_at(uint32_t addr, f32x2& a, f32x2& b) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+%3];" : "=l"(a), "=l"(b) : "r"(addr), "n"(OFF));
+}
+template <typename T, int OFF>
+__device__ __forceinline__ void lds_chunk8_at(uint32_t a, P8& t) {
+    if constexpr (sizeof(T) == 4) {
+        const uint32_t a2 = a ^ 16u;
+        lds_pairs_at<OFF>(a, t.q[0], t.q[1]);
+        lds_pairs_at<OFF>(a2, t.q[2], t.q[3]);
+    } else {
+        lds_chunk8<T>(a + OFF, t);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host side: tensor maps of the source feature maps (one per view), box {C, BW, TILE_H + BH_EXTRA, 1}
 // ---------------------------------------------------------------------------------------------------------------------
