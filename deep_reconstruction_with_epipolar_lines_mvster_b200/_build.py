@@ -38,8 +38,8 @@ def _sources():
 
 def _digest(path: str) -> str:
     h = hashlib.sha1()
-    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "epi_common.cuh"), os.path.join(CSRC, "epi_tma.cuh"), os.path.join(CSRC, "tail_common.cuh"),
-                os.path.join(INCLUDE, "mvster_b200.h")]:
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    for dep in [path] + headers + [os.path.join(INCLUDE, "mvster_b200.h")]:
         with open(dep, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())

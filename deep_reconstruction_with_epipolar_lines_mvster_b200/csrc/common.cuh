@@ -39,6 +39,21 @@ static inline int ensure_dynamic_smem(Kernel kernel, int bytes, bool (&done)[64]
     return MVSTER_OK;
 }
 
+// Same for kernels whose dynamic shared-memory size depends on run-time arguments: remembers the largest size set
+// per device and raises the limit again when a later call needs more.  Safe to call from concurrent host threads.
+template <typename Kernel>
+static inline int ensure_dynamic_smem_bytes(Kernel kernel, int bytes, int (&largest)[64], const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (__atomic_load_n(&largest[dev], __ATOMIC_ACQUIRE) >= bytes) return MVSTER_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return check_cuda(e, what);
+    int seen = __atomic_load_n(&largest[dev], __ATOMIC_ACQUIRE);
+    while (seen < bytes && !__atomic_compare_exchange_n(&largest[dev], &seen, bytes, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+    }
+    return MVSTER_OK;
+}
+
 #define MVSTER_CHECK_LAUNCH(what)                                   \
     do {                                                            \
         cudaError_t e__ = cudaGetLastError();                       \

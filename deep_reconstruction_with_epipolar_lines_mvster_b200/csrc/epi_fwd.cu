@@ -28,6 +28,8 @@
 #include <stdlib.h>
 
 #include "epi_tma.cuh"
+#include "epi_fwd_box.cuh"
+#include "epi_fwd_pipe.cuh"
 
 namespace mvster {
 
@@ -672,22 +674,47 @@ static int launch_line(const EpiFwdParams& p, cudaStream_t stream) {
     return MVSTER_OK;
 }
 
+// environment switches, read once per process (development A/B and the fallback tests)
+struct FwdEnv {
+    bool no_tma, no_line, fine_v1, no_pipe;
+    FwdEnv() : no_tma(getenv("MVSTER_NO_TMA") != nullptr), no_line(getenv("MVSTER_NO_LINE") != nullptr),
+               fine_v1(getenv("MVSTER_FINE_V1") != nullptr), no_pipe(getenv("MVSTER_PIPE") == nullptr) {}
+};
+static const FwdEnv& fwd_env() {
+    static const FwdEnv e;
+    return e;
+}
+
 template <int C, int CPG, int D>
 static int dispatch_variant(EpiFwdParams& p, int dtype, bool allow_tma, cudaStream_t s) {
+    const FwdEnv& env = fwd_env();
+    if constexpr (C <= 16) {
+        // fine stages (16/32/64-byte texels): TMA-staged box kernel when the tensor maps can be built
+        if (allow_tma && !env.fine_v1) {
+            bool built = false;
+            if (!env.no_pipe) {  // persistent pipelined kernel (needs scratch for the tile boxes)
+                const int st = dtype == MVSTER_BF16 ? launch_pipe<C, CPG, D, __nv_bfloat16>(p, s, &built)
+                                                    : launch_pipe<C, CPG, D, float>(p, s, &built);
+                if (built || st != MVSTER_OK) return st;
+            }
+            const int st = dtype == MVSTER_BF16 ? launch_box<C, CPG, D, __nv_bfloat16>(p, s, &built)
+                                                : launch_box<C, CPG, D, float>(p, s, &built);
+            if (built || st != MVSTER_OK) return st;
+        }
+    }
     if (dtype == MVSTER_BF16) {
-        if constexpr (C <= 16) {  // 16/32-byte bf16 texels (fine stages): the same TMA-staged swizzled-box gather
+        if constexpr (C <= 16) {  // first-generation staged kernel (MVSTER_FINE_V1=1)
             if (allow_tma && make_maps<C, CPG, D, __nv_bfloat16>(p.tmap, p.src, p.Nsrc, p.B, p.Hs, p.Ws))
                 return launch_fwd<C, CPG, D, true, __nv_bfloat16>(p, s);
         }
         return launch_direct<C, CPG, D, __nv_bfloat16>(p, s);
     }
     if constexpr (C == 8 || C == 16) {
-        // fine stages (32/64-byte fp32 texels): TMA-staged shared-memory gather when the tensor maps can be built
         if (allow_tma && make_maps<C, CPG, D, float>(p.tmap, p.src, p.Nsrc, p.B, p.Hs, p.Ws)) return launch_fwd<C, CPG, D, true, float>(p, s);
     }
     if constexpr (C == 32 && CPG <= 4) {
         // whole-line texels: conflict-free rotated shared-memory gather (see epi_fwd_line_kernel)
-        if (allow_tma && getenv("MVSTER_NO_LINE") == nullptr && make_line_maps(p, p.Nsrc, p.B, p.Hs, p.Ws))
+        if (allow_tma && !env.no_line && make_line_maps(p, p.Nsrc, p.B, p.Hs, p.Ws))
             return launch_line<CPG, D>(p, s);
     }
     return launch_direct<C, CPG, D, float>(p, s);
@@ -704,6 +731,11 @@ static int dispatch_d(EpiFwdParams& p, int D, int dtype, bool allow_tma, cudaStr
 
 template <int C>
 static int dispatch_cpg(EpiFwdParams& p, int cpg, int D, int dtype, bool allow_tma, cudaStream_t s) {
+#ifdef MVSTER_FAST_BUILD  // development builds (scripts/build_variant.py): only the shipped (C, C/G) pairs
+    constexpr int kCpg = C == 64 ? 8 : (C == 32 ? 4 : (C == 16 ? 4 : 2));
+    if (cpg != kCpg) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: MVSTER_FAST_BUILD has C/G=%d only for C=%d", kCpg, C);
+    return dispatch_d<C, kCpg>(p, D, dtype, allow_tma, s);
+#else
     switch (cpg) {
         case 1: return dispatch_d<C, 1>(p, D, dtype, allow_tma, s);
         case 2: return dispatch_d<C, 2>(p, D, dtype, allow_tma, s);
@@ -711,6 +743,7 @@ static int dispatch_cpg(EpiFwdParams& p, int cpg, int D, int dtype, bool allow_t
         case 8: return dispatch_d<C, 8>(p, D, dtype, allow_tma, s);
         default: return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: C/G=%d not in {1,2,4,8}", cpg);
     }
+#endif
 }
 
 }  // namespace mvster
@@ -748,7 +781,7 @@ extern "C" int mvster_epi_fwd(const void* ref, const void* const* src, const flo
     p.inv_sqrt_c = (float)(1.0 / sqrt((double)C));
     DeviceGuard guard(out);
     if (guard.status != MVSTER_OK) return guard.status;
-    const bool allow_tma = getenv("MVSTER_NO_TMA") == nullptr;
+    const bool allow_tma = !fwd_env().no_tma;
     const int cpg = C / G;
     cudaStream_t s = (cudaStream_t)stream;
     switch (C) {

@@ -25,7 +25,8 @@ def cc(src):
     return obj
 
 
-B.build_library()
+if not os.environ.get('MVSTER_VARIANT_NO_MAIN'):
+    B.build_library()  # parallel invocations: build the main library once first and set MVSTER_VARIANT_NO_MAIN=1
 with ThreadPoolExecutor(4) as ex:
     objs = list(ex.map(cc, ONLY))
 objs += [os.path.join(B.BUILD_DIR, s[:-3] + ".o") for s in B._sources() if s not in ONLY]

@@ -1,0 +1,8 @@
+#!/bin/bash
+# ncu --set full on the box kernels (stage 3 + stage 4 K1 forward) of one cascade step; plain run first
+set -u
+mkdir -p gpurun_out
+CMD="python scripts/bench_k1.py --iters 2 --tag ncu"
+$CMD > gpurun_out/ncu_box_plain.log 2>&1 || { echo plain run failed; tail -5 gpurun_out/ncu_box_plain.log; exit 1; }
+ncu --set full --clock-control none --import-source on -k regex:epi_fwd_box -s 6 -c 2 -f -o gpurun_out/k1_box $CMD > gpurun_out/ncu_box.log 2>&1
+echo "ncu exit $?"; tail -3 gpurun_out/ncu_box.log
