@@ -1,8 +1,6 @@
 // Host-side plumbing of libmvster_b200: thread-local error string, launch counter, device guard, version.
 #include <stdarg.h>
 #include <atomic>
-#include <mutex>
-#include <vector>
 
 #include "common.cuh"
 
@@ -60,47 +58,6 @@ DeviceGuard::DeviceGuard(const void* ptr) {
 
 DeviceGuard::~DeviceGuard() {
     if (prev >= 0 && dev >= 0 && prev != dev) cudaSetDevice(prev);
-}
-
-// Scratch buffers of kernels that need one (K1 forward: per-tile bounding boxes).  One grow-only allocation per
-// (device, stream): launches on one stream reuse it in stream order, launches on different streams never share it.
-struct Workspace {
-    int dev;
-    cudaStream_t stream;
-    void* ptr;
-    size_t bytes;
-};
-static std::mutex g_ws_mutex;
-static std::vector<Workspace> g_ws;
-
-void* epi_workspace(cudaStream_t stream, size_t bytes, int* status) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-    std::lock_guard<std::mutex> lock(g_ws_mutex);
-    Workspace* w = nullptr;
-    for (auto& e : g_ws)
-        if (e.dev == dev && e.stream == stream) { w = &e; break; }
-    if (w && w->bytes >= bytes) return w->ptr;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cudaGetLastError();
-    if (cap != cudaStreamCaptureStatusNone) {
-        *status = fail(MVSTER_ERR_CUDA, "epi_fwd: scratch of %zu bytes must be allocated outside CUDA graph capture; "
-                       "run the same call once eagerly on this stream first", bytes);
-        return nullptr;
-    }
-    const size_t want = bytes + bytes / 4 + 4096;
-    void* ptr = nullptr;
-    cudaError_t e = cudaMalloc(&ptr, want);
-    if (e != cudaSuccess) { *status = check_cuda(e, "epi_fwd: cudaMalloc(scratch)"); return nullptr; }
-    if (w) {
-        // the old buffer may still be read by kernels in flight on this stream
-        cudaStreamSynchronize(stream);
-        cudaFree(w->ptr);
-        w->ptr = ptr; w->bytes = want;
-    } else {
-        g_ws.push_back(Workspace{dev, stream, ptr, want});
-    }
-    return ptr;
 }
 
 }  // namespace mvster

@@ -29,309 +29,8 @@
 
 #include "epi_tma.cuh"
 #include "epi_fwd_box.cuh"
-#include "epi_fwd_pipe.cuh"
 
 namespace mvster {
-
-// ---------------------------------------------------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------------------------------------------------
-template <int C, int CPG, int D, bool TMA, typename T>
-__global__ void __launch_bounds__(Split<C, CPG, D, (int)sizeof(T)>::WARPS * 32, Split<C, CPG, D, (int)sizeof(T)>::MINB)
-    epi_fwd_kernel(const __grid_constant__ EpiFwdParams p) {
-    using S = Split<C, CPG, D, (int)sizeof(T)>;
-    using Gm = TmaGeom<C, (int)sizeof(T)>;
-    constexpr int CH = S::CH, DL = S::DL, LC = S::LC, L = S::L, PPW = S::PPW, GPL = S::GPL, NCHUNK = S::NCHUNK;
-    constexpr int G = C / CPG;
-    constexpr int WX = S::WX, TILE_H = S::TILE_H;  // CTA tile: 32 x 8 pixels
-    constexpr int TB = C * (int)sizeof(T); // texel bytes
-    static_assert(!TMA || (TB >= 16 && TB <= 64 && LC == 1 && S::TILE_W == 32), "TMA variant: 16/32/64-byte texels");
-    constexpr uint32_t CHB = 8u * (uint32_t)sizeof(T);  // bytes of one 8-channel chunk
-
-    extern __shared__ unsigned char smem_raw[];
-    // TMA variant: [buf0 | buf1] 1024-aligned, then 2 mbarriers + 3 bbox slots; both variants: homographies at the end
-    constexpr int BH = (TILE_H + Gm::BH_EXTRA);
-    constexpr int BUF_BYTES = TMA ? Gm::BW * BH * TB : 0;
-    constexpr int ROW_BYTES = Gm::BW * TB;
-    const uint32_t smem_base = TMA ? ((smem_u32(smem_raw) + 1023u) & ~1023u) : smem_u32(smem_raw);
-    const uint32_t ctl = smem_base + 2u * BUF_BYTES;
-    unsigned char* ctl_ptr = smem_raw + (ctl - smem_u32(smem_raw));
-    int* bbox = reinterpret_cast<int*>(ctl_ptr + 16);                                  // [3][4] (TMA only)
-    float* rt_s = reinterpret_cast<float*>(ctl_ptr + (TMA ? Gm::CTL_BYTES : 0));  // [Nsrc][12]
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int pix = lane / L;
-    const int cl = lane % LC;         // channel chunk of this lane
-    const int dl = (lane % L) / LC;   // hypothesis chunk of this lane
-    const int b = blockIdx.z;
-    for (int i = tid; i < p.Nsrc * 12; i += S::WARPS * 32) rt_s[i] = __ldg(p.rt + (size_t)b * p.Nsrc * 12 + i);
-    int x = blockIdx.x * S::TILE_W + (warp % WX) * PPW + pix;
-    int y = blockIdx.y * TILE_H + (warp / WX);
-    const bool live = (x < p.W) && (y < p.H);
-    x = min(x, p.W - 1);  // dead lanes shadow a valid pixel: shuffles stay convergent, the bounding box is unaffected
-    y = min(y, p.H - 1);
-
-    if constexpr (TMA) {
-        if (tid == 0) {
-            mbar_init(ctl, 1);
-            mbar_init(ctl + 8, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                bbox[i * 4 + 0] = INT_MAX; bbox[i * 4 + 1] = INT_MAX;
-                bbox[i * 4 + 2] = INT_MIN; bbox[i * 4 + 3] = INT_MIN;
-            }
-        }
-    }
-    __syncthreads();
-
-    const size_t plane = (size_t)p.H * p.W;
-    const size_t pix_off = (size_t)y * p.W + x;
-
-    // reference channels of this lane as packed pairs, pre-scaled by 1/(C/G) so the group mean is a plain sum
-    f32x2 rf[NCHUNK * 4];
-    {
-        const T* refp = reinterpret_cast<const T*>(p.ref) + (((size_t)b * plane + pix_off) * C + cl * CH);
-        const f32x2 sc = pack2(1.0f / CPG, 1.0f / CPG);
-#pragma unroll
-        for (int k = 0; k < NCHUNK; ++k) {
-            const P8 r = load_pairs<T>(refp + k * 8);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rf[k * 4 + q] = mul2(r.q[q], sc);
-        }
-    }
-    float hyp[DL];
-#pragma unroll
-    for (int d = 0; d < DL; ++d) hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + dl * DL + d) * plane + pix_off);
-
-    float acc[GPL][DL], wsum[DL];
-#pragma unroll
-    for (int d = 0; d < DL; ++d) {
-        wsum[d] = 1e-8f;  // reference :1037
-#pragma unroll
-        for (int g = 0; g < GPL; ++g) acc[g][d] = 0.0f;
-    }
-
-    const float fxp = (float)x, fyp = (float)y;
-    const float wlim = (float)p.Ws, hlim = (float)p.Hs;
-    const size_t lane_src_off = ((size_t)b * p.Hs * p.Ws * C + cl * CH) * sizeof(T);
-
-    // ---- TMA staging state (one view ahead) ----------------------------------------------------------------------
-    float nsx[DL], nsy[DL];
-    int nbx = 0, nby = 0;
-    bool nfit = false;
-    uint32_t uses0 = 0, uses1 = 0;  // completed phases of the two mbarriers (uniform across the CTA)
-
-    auto positions = [&](int v, float* sx, float* sy) {
-        const Homography h = homography_from_smem(rt_s + v * 12);
-        // R * [x, y, 1]^T, shared by all hypotheses of this pixel (reference :42)
-        const float ax = fmaf(h.r00, fxp, fmaf(h.r01, fyp, h.r02));
-        const float ay = fmaf(h.r10, fxp, fmaf(h.r11, fyp, h.r12));
-        const float az = fmaf(h.r20, fxp, fmaf(h.r21, fyp, h.r22));
-#pragma unroll
-        for (int d = 0; d < DL; ++d) sample_pos(ax, ay, az, h, hyp[d], wlim, hlim, sx[d], sy[d]);
-    };
-
-    auto stage_view = [&](int v) {  // TMA only: positions of view v, CTA bounding box, TMA request; one __syncthreads()
-        positions(v, nsx, nsy);
-        float lox = nsx[0], hix = nsx[0], loy = nsy[0], hiy = nsy[0];
-#pragma unroll
-        for (int d = 1; d < DL; ++d) {
-            lox = fminf(lox, nsx[d]); hix = fmaxf(hix, nsx[d]);
-            loy = fminf(loy, nsy[d]); hiy = fmaxf(hiy, nsy[d]);
-        }
-        const int slot = v % 3;
-        bbox_update(&bbox[slot * 4], lox, loy, hix, hiy, lane);
-        if (tid == 0) {  // recycle the slot that view v+1 will use (its last readers passed the previous barrier)
-            const int nx = (v + 1) % 3;
-            bbox[nx * 4 + 0] = INT_MAX; bbox[nx * 4 + 1] = INT_MAX;
-            bbox[nx * 4 + 2] = INT_MIN; bbox[nx * 4 + 3] = INT_MIN;
-        }
-        __syncthreads();  // bbox complete; every thread has also finished gathering from buffer v&1 (view v-2)
-        const int4 bb = *reinterpret_cast<const int4*>(&bbox[slot * 4]);
-        nbx = bb.x; nby = bb.y;
-        nfit = (bb.z - bb.x + 2 <= Gm::BW) && (bb.w - bb.y + 2 <= BH);  // +1 for the right / bottom tap
-        if (nfit && tid == 0) {
-            const uint32_t bar = ctl + 8u * (v & 1);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
-            mbar_expect_tx(bar, (uint32_t)BUF_BYTES);
-            tma_load_4d(smem_base + (uint32_t)BUF_BYTES * (v & 1), &p.tmap[v], bar, 0, nbx, nby, b);
-        }
-    };
-
-    if constexpr (TMA) stage_view(0);
-
-#pragma unroll 1
-    for (int v = 0; v < p.Nsrc; ++v) {
-        float sx[DL], sy[DL];
-        int bx = 0, by = 0;
-        bool fit = false;
-        if constexpr (TMA) {
-#pragma unroll
-            for (int d = 0; d < DL; ++d) { sx[d] = nsx[d]; sy[d] = nsy[d]; }
-            bx = nbx; by = nby; fit = nfit;
-            if (v + 1 < p.Nsrc) stage_view(v + 1);
-        } else {
-            positions(v, sx, sy);
-        }
-
-        float cor[GPL][DL];
-        if (TMA && fit) {
-            // ---- gather from the swizzled shared-memory box (zero-filled outside the image) --------------------------
-            const uint32_t parity = ((v & 1) ? uses1 : uses0) & 1u;
-            mbar_wait(ctl + 8u * (v & 1), parity);
-            if (v & 1) ++uses1; else ++uses0;
-            const uint32_t buf = smem_base + (uint32_t)BUF_BYTES * (v & 1);
-            constexpr uint32_t SWZ = (uint32_t)(TB / 16 - 1) << 4;  // swizzled chunk-index bits: [4] or [5:4]
-            if constexpr (NCHUNK == 1 && MVSTER_CELL_REUSE) {
-                // Consecutive hypotheses of a pixel are sub-texel to ~1 texel apart at the fine stages: when sample d
-                // falls into the same 2x2 texel cell as sample d-1 its taps are already in registers.  Neighbouring
-                // pixels change cell at the same hypothesis, so whole quarter-warps skip the LDS together.
-                P8 t00, t01, t10, t11;
-                int prx = INT_MIN, pry = INT_MIN;
-#pragma unroll
-                for (int d = 0; d < DL; ++d) {
-                    float x0f, y0f;
-                    int x0i, y0i;
-                    floor_fi(sx[d], x0f, x0i);
-                    floor_fi(sy[d], y0f, y0i);
-                    const float fx = sx[d] - x0f, fy = sy[d] - y0f;
-                    const int rx = x0i - bx, ry = y0i - by;
-                    if (d == 0 || rx != prx || ry != pry) {
-                        // the swizzle bits come from the x offset only (buffer and rows are multiples of 512 bytes), so
-                        // they can be taken from the address itself; the lower row is an immediate offset
-                        static_assert(SWZ == 0 || (ROW_BYTES % 512 == 0 && BUF_BYTES % 512 == 0), "swizzle phase must depend on x only");
-                        const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + (uint32_t)rx * TB, baseR = base + TB;
-                        const uint32_t aL = base ^ ((base >> 3) & SWZ), aR = baseR ^ ((baseR >> 3) & SWZ);
-                        lds_chunk8_at<T, 0>(aL, t00);
-                        lds_chunk8_at<T, 0>(aR, t01);
-                        lds_chunk8_at<T, ROW_BYTES>(aL, t10);
-                        lds_chunk8_at<T, ROW_BYTES>(aR, t11);
-                    }
-                    prx = rx; pry = ry;
-                    const float gx = 1.0f - fx, gy = 1.0f - fy;
-                    float cg[8 / CPG];
-                    blend_correlate<CPG>(t00, t01, t10, t11, gx * gy, fx * gy, gx * fy, fx * fy, rf, cg);
-#pragma unroll
-                    for (int g = 0; g < 8 / CPG; ++g) cor[g][d] = cg[g];
-                }
-            } else {
-#pragma unroll
-            for (int d = 0; d < DL; ++d) {
-                float x0f, y0f;
-                int x0i, y0i;
-                floor_fi(sx[d], x0f, x0i);
-                floor_fi(sy[d], y0f, y0i);
-                const float fx = sx[d] - x0f, fy = sy[d] - y0f;
-                const int rx = x0i - bx, ry = y0i - by;
-                const uint32_t xo = (uint32_t)rx * TB;  // byte offset of the left texel inside its row
-                const uint32_t base = buf + (uint32_t)ry * ROW_BYTES + xo;
-                // hardware swizzle: 16-byte chunk index ^= address bits [8:7] (64B mode) / [7] (32B mode); rows are a
-                // multiple of 512 bytes and the buffer is 1024-aligned, so those bits come from the x offset only
-                const uint32_t mA = (xo >> 3) & SWZ, mB = ((xo + TB) >> 3) & SWZ;
-                const float gx = 1.0f - fx, gy = 1.0f - fy;
-                const float w00 = gx * gy, w01 = fx * gy, w10 = gx * fy, w11 = fx * fy;
-#pragma unroll
-                for (int k = 0; k < NCHUNK; ++k) {
-                    const uint32_t aL = (base + CHB * k) ^ mA, aR = (base + TB + CHB * k) ^ mB;
-                    P8 t00, t01, t10, t11;
-                    lds_chunk8<T>(aL, t00);
-                    lds_chunk8<T>(aR, t01);
-                    lds_chunk8<T>(aL + ROW_BYTES, t10);
-                    lds_chunk8<T>(aR + ROW_BYTES, t11);
-                    float cg[8 / CPG];
-                    blend_correlate<CPG>(t00, t01, t10, t11, w00, w01, w10, w11, rf + k * 4, cg);
-#pragma unroll
-                    for (int g = 0; g < 8 / CPG; ++g) cor[k * (8 / CPG) + g][d] = cg[g];
-                }
-            }
-            }
-        } else {
-            // ---- direct gather from global memory, per-tap bounds weights --------------------------------------------
-            const char* srcp = reinterpret_cast<const char*>(p.src[v]) + lane_src_off;
-#pragma unroll
-            for (int d = 0; d < DL; ++d) {
-                const float x0f = floorf(sx[d]), y0f = floorf(sy[d]);
-                const float fx = sx[d] - x0f, fy = sy[d] - y0f;
-                const int x0 = (int)x0f, y0 = (int)y0f;  // in [-1, Ws] x [-1, Hs] after the clamp
-                const bool vx0 = (unsigned)x0 < (unsigned)p.Ws, vx1 = (unsigned)(x0 + 1) < (unsigned)p.Ws;
-                const bool vy0 = (unsigned)y0 < (unsigned)p.Hs, vy1 = (unsigned)(y0 + 1) < (unsigned)p.Hs;
-                const int xc0 = min(max(x0, 0), p.Ws - 1), xc1 = min(x0 + 1, p.Ws - 1);
-                const int yc0 = min(max(y0, 0), p.Hs - 1), yc1 = min(y0 + 1, p.Hs - 1);
-                const float gx = vx0 ? 1.0f - fx : 0.0f, hx = vx1 ? fx : 0.0f;
-                const float gy = vy0 ? 1.0f - fy : 0.0f, hy = vy1 ? fy : 0.0f;
-                const float w00 = gx * gy, w01 = hx * gy, w10 = gx * hy, w11 = hx * hy;
-                // texel index < 2^31 / C (checked on the host): 32-bit index, one IMAD.WIDE.U32 per address
-                const unsigned r0 = (unsigned)(yc0 * p.Ws), r1 = (unsigned)(yc1 * p.Ws);
-                const char* a00 = srcp + (size_t)(r0 + (unsigned)xc0) * TB;
-                const char* a01 = srcp + (size_t)(r0 + (unsigned)xc1) * TB;
-                const char* a10 = srcp + (size_t)(r1 + (unsigned)xc0) * TB;
-                const char* a11 = srcp + (size_t)(r1 + (unsigned)xc1) * TB;
-#pragma unroll
-                for (int k = 0; k < NCHUNK; ++k) {
-                    constexpr int KO = 8 * (int)sizeof(T);
-                    const P8 t00 = load_pairs<T>(a00 + k * KO), t01 = load_pairs<T>(a01 + k * KO);
-                    const P8 t10 = load_pairs<T>(a10 + k * KO), t11 = load_pairs<T>(a11 + k * KO);
-                    float cg[8 / CPG];
-                    blend_correlate<CPG>(t00, t01, t10, t11, w00, w01, w10, w11, rf + k * 4, cg);
-#pragma unroll
-                    for (int g = 0; g < 8 / CPG; ++g) cor[k * (8 / CPG) + g][d] = cg[g];
-                }
-            }
-        }
-
-        // score[d] = sum over all G groups (reference cor_feat.sum(1), :1083): lane-local, then the channel lanes
-        float score[DL];
-#pragma unroll
-        for (int d = 0; d < DL; ++d) {
-            float s = cor[0][d];
-#pragma unroll
-            for (int g = 1; g < GPL; ++g) s += cor[g][d];
-            score[d] = s;
-        }
-#pragma unroll
-        for (int m = 1; m < LC; m <<= 1) {
-#pragma unroll
-            for (int d = 0; d < DL; ++d) score[d] += __shfl_xor_sync(0xffffffffu, score[d], m);
-        }
-        // softmax over D of score / attn_temp, then / sqrt(C); max and sum cross the hypothesis lanes
-        float mx = score[0];
-#pragma unroll
-        for (int d = 1; d < DL; ++d) mx = fmaxf(mx, score[d]);
-#pragma unroll
-        for (int m = LC; m < L; m <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-        float e[DL], es = 0.0f;
-#pragma unroll
-        for (int d = 0; d < DL; ++d) {
-            e[d] = ex2_approx((score[d] - mx) * p.score_scale);
-            es += e[d];
-        }
-#pragma unroll
-        for (int m = LC; m < L; m <<= 1) es += __shfl_xor_sync(0xffffffffu, es, m);
-        const float norm = __fdividef(p.inv_sqrt_c, es);
-#pragma unroll
-        for (int d = 0; d < DL; ++d) {
-            const float w = e[d] * norm;
-            wsum[d] += w;
-#pragma unroll
-            for (int g = 0; g < GPL; ++g) acc[g][d] = fmaf(w, cor[g][d], acc[g][d]);
-            if (p.weights != nullptr && cl == 0 && live)
-                p.weights[(((size_t)b * p.Nsrc + v) * D + dl * DL + d) * plane + pix_off] = w;
-        }
-    }
-
-    if (!live) return;
-#pragma unroll
-    for (int d = 0; d < DL; ++d) {
-        const float inv = __frcp_rn(wsum[d]);
-        const int dd = dl * DL + d;
-#pragma unroll
-        for (int g = 0; g < GPL; ++g)
-            stg_stream(p.out + (((size_t)b * G + cl * GPL + g) * D + dd) * plane + pix_off, acc[g][d] * inv);
-        if (p.wsum != nullptr && cl == 0) p.wsum[((size_t)b * D + dd) * plane + pix_off] = wsum[d];
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // LINE kernel (fp32, C = 32: a texel is exactly one 128-byte line).  Through L1 a warp-wide gather of whole-line
@@ -622,27 +321,6 @@ __global__ void __launch_bounds__(LineGeom::WARPS * 32, MVSTER_LINE_MINB) epi_fw
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
-template <int C, int CPG, int D, bool TMA, typename T>
-static int launch_fwd(const EpiFwdParams& p, cudaStream_t stream) {
-    using S = Split<C, CPG, D, (int)sizeof(T)>;
-    using Gm = TmaGeom<C, (int)sizeof(T)>;
-    constexpr int TILE_H = S::TILE_H;
-    constexpr int TB = C * (int)sizeof(T);
-    const int smem = MVSTER_MAX_SRC_VIEWS * 48 +
-                     (TMA ? 2 * Gm::BW * (TILE_H + Gm::BH_EXTRA) * TB + 1024 + Gm::CTL_BYTES : 0);
-    static bool attr_done[64] = {};
-    if (smem > 48 * 1024) {
-        const int st = ensure_dynamic_smem(epi_fwd_kernel<C, CPG, D, TMA, T>, smem, attr_done, "epi_fwd: cudaFuncSetAttribute");
-        if (st != MVSTER_OK) return st;
-    }
-    dim3 grid((p.W + S::TILE_W - 1) / S::TILE_W, (p.H + TILE_H - 1) / TILE_H, p.B);
-    if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");
-    epi_fwd_kernel<C, CPG, D, TMA, T><<<grid, S::WARPS * 32, smem, stream>>>(p);
-    count_launch();
-    MVSTER_CHECK_LAUNCH("epi_fwd launch");
-    return MVSTER_OK;
-}
-
 static bool make_line_maps(EpiFwdParams& p, int Nsrc, int B, int Hs, int Ws) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return false;
@@ -674,11 +352,10 @@ static int launch_line(const EpiFwdParams& p, cudaStream_t stream) {
     return MVSTER_OK;
 }
 
-// environment switches, read once per process (development A/B and the fallback tests)
+// environment switches, read once per process (the fallback tests)
 struct FwdEnv {
-    bool no_tma, no_line, fine_v1, no_pipe;
-    FwdEnv() : no_tma(getenv("MVSTER_NO_TMA") != nullptr), no_line(getenv("MVSTER_NO_LINE") != nullptr),
-               fine_v1(getenv("MVSTER_FINE_V1") != nullptr), no_pipe(getenv("MVSTER_PIPE") == nullptr) {}
+    bool no_tma, no_line;
+    FwdEnv() : no_tma(getenv("MVSTER_NO_TMA") != nullptr), no_line(getenv("MVSTER_NO_LINE") != nullptr) {}
 };
 static const FwdEnv& fwd_env() {
     static const FwdEnv e;
@@ -690,28 +367,14 @@ static int dispatch_variant(EpiFwdParams& p, int dtype, bool allow_tma, cudaStre
     const FwdEnv& env = fwd_env();
     if constexpr (C <= 16) {
         // fine stages (16/32/64-byte texels): TMA-staged box kernel when the tensor maps can be built
-        if (allow_tma && !env.fine_v1) {
+        if (allow_tma) {
             bool built = false;
-            if (!env.no_pipe) {  // persistent pipelined kernel (needs scratch for the tile boxes)
-                const int st = dtype == MVSTER_BF16 ? launch_pipe<C, CPG, D, __nv_bfloat16>(p, s, &built)
-                                                    : launch_pipe<C, CPG, D, float>(p, s, &built);
-                if (built || st != MVSTER_OK) return st;
-            }
             const int st = dtype == MVSTER_BF16 ? launch_box<C, CPG, D, __nv_bfloat16>(p, s, &built)
                                                 : launch_box<C, CPG, D, float>(p, s, &built);
             if (built || st != MVSTER_OK) return st;
         }
     }
-    if (dtype == MVSTER_BF16) {
-        if constexpr (C <= 16) {  // first-generation staged kernel (MVSTER_FINE_V1=1)
-            if (allow_tma && make_maps<C, CPG, D, __nv_bfloat16>(p.tmap, p.src, p.Nsrc, p.B, p.Hs, p.Ws))
-                return launch_fwd<C, CPG, D, true, __nv_bfloat16>(p, s);
-        }
-        return launch_direct<C, CPG, D, __nv_bfloat16>(p, s);
-    }
-    if constexpr (C == 8 || C == 16) {
-        if (allow_tma && make_maps<C, CPG, D, float>(p.tmap, p.src, p.Nsrc, p.B, p.Hs, p.Ws)) return launch_fwd<C, CPG, D, true, float>(p, s);
-    }
+    if (dtype == MVSTER_BF16) return launch_direct<C, CPG, D, __nv_bfloat16>(p, s);
     if constexpr (C == 32 && CPG <= 4) {
         // whole-line texels: conflict-free rotated shared-memory gather (see epi_fwd_line_kernel)
         if (allow_tma && !env.no_line && make_line_maps(p, p.Nsrc, p.B, p.Hs, p.Ws))

@@ -1,26 +1,26 @@
-// K1 forward, fine stages (texels of 16 / 32 / 64 bytes: C = 8 / 16, fp32 or bf16): the staged "box" kernels.
+// K1 forward, fine stages (texels of 16 / 32 / 64 bytes: C = 8 / 16, fp32 or bf16): the staged "box" kernel.
 //
 // A CTA owns a 32 x TILE_H pixel tile.  Per source view the texels its samples can touch are staged by ONE
 // cp.async.bulk.tensor.4d of box {C, BW, BH, 1} into shared memory (TMA zero-fill outside the image IS grid_sample's
-// padding_mode='zeros', so the gather has no bounds logic), and every lane gathers its four bilinear taps with LDS.128
+// padding_mode='zeros', so the gather has no bounds logic), and every lane gathers its bilinear taps with LDS.128
 // from the hardware-swizzled box (8 neighbouring texels hit 8 different bank groups).
 //
-// Measured facts that shaped this file (profiles/r02_k1_fwd_*.md):
-//   * first version (r01): 147 warp instructions per (pixel, view, hypothesis) sample, one CTA barrier per view.
-//     Knock-out builds showed where the time goes: without the gather LDS -12 %, without the blend math 0 %, without
-//     both -27 %; the remaining 73 % was everything AROUND the gather (sample arithmetic, bounding boxes, barriers,
-//     start-up latency of short-lived CTAs at 16 warps per SM).
-//   * sample arithmetic is therefore done in packed fp32x2 across PAIRS of hypotheses (p = R [x y 1]^T d + t, Newton
-//     step of the reciprocal, floor via FADD2.RM with 1.5 * 2^23 - box origin - which yields the floor and the
-//     box-relative integer index at once -, fractions, the four bilinear weights): 12.5 instead of 26 issue slots per
-//     sample; the tap address is two integer multiply-adds of the raw float bits.
+// Measured facts that shaped this file (profiles/r02_k1_fwd_stage4.md):
+//   * r01 version: 147 warp instructions per (pixel, view, hypothesis) sample, one CTA barrier per view.  Knock-out
+//     builds: without the gather LDS -12 %, without the blend math 0 %, without both -27 %; the remaining 73 % was
+//     everything AROUND the gather.  The kernel is bound by issue slots (70 %) and the shared-memory data pipe (75 %)
+//     together, so both instruction count and LDS wavefronts are what is optimised here.
+//   * sample arithmetic runs packed (fp32x2) across PAIRS of hypotheses: p = R [x y 1]^T d + t, Newton step of the
+//     reciprocal, floor via FADD2.RM with 1.5 * 2^23 - box origin (yields floor and box-relative index at once).
+//   * the exact bounding box of a view needs only the two extreme hypotheses of every pixel (the sample position is a
+//     Moebius function of the depth: monotone between the extremes as long as z keeps its sign); the per-warp boxes go
+//     to shared memory with REDUX + one store, warp 0 combines them, plans all views at once (one lane per view:
+//     descriptor + TMA request) and the other warps pick the plan up behind the view's mbarrier - no atomics, no
+//     per-thread re-derivation of the box.
+//   * texel-column register slots (gather_view_slots): 3.85 instead of 8 texel columns per pixel and view.
+//   * softmax / aggregation packed across hypothesis pairs.
 //   * no clamps, no zero test and no bounds logic on the staged path: a view whose bounding box is larger than the
 //     staging buffer - which includes every non-finite position - takes the exact direct-gather path for that tile.
-//
-// Two kernels share the per-view device functions below:
-//   epi_fwd_box_kernel  (this file): one tile per CTA, exact per-view bounding box computed in the kernel (phase A).
-//   epi_fwd_pipe_kernel (epi_fwd_pipe.cuh): persistent CTAs, boxes from a tiny pre-pass, TMA ring with full / empty
-//                        mbarriers fed one tile ahead - no CTA-wide barrier in the steady state.
 #pragma once
 
 #include "epi_tma.cuh"
@@ -38,7 +38,7 @@
 #define MVSTER_BOX_BHX 3
 #endif
 #ifndef MVSTER_BOX_NBUF
-#define MVSTER_BOX_NBUF 4
+#define MVSTER_BOX_NBUF 3   // A/B (stage 4 / stage 3): 4 buffers 0.679 / 0.391 ms, 3 buffers 0.658 / 0.333 ms (64-byte texels: 3 CTAs per SM instead of 2)
 #endif
 #ifndef MVSTER_BOX_WIDE_WARPS
 #define MVSTER_BOX_WIDE_WARPS 8
@@ -46,16 +46,13 @@
 #ifndef MVSTER_BOX_WIDE_MINB
 #define MVSTER_BOX_WIDE_MINB 3
 #endif
-#ifndef MVSTER_BOX_SLOTS
-#define MVSTER_BOX_SLOTS 1  // texel-column register slots shared by the hypotheses of a pixel (gather_view_slots); 0 = gather every tap
-#endif
 #ifndef MVSTER_BOX_KO
-#define MVSTER_BOX_KO 0    // development only, wrong results: knock-out bits (1 no gather LDS, 2 no TMA, 8 no stores, 16 no blend math)
+#define MVSTER_BOX_KO 0    // development only, WRONG RESULTS: knock-out bits (1: no gather LDS, 2: no TMA - the boxes hold garbage, 4: no blend math)
 #endif
 
 namespace mvster {
 
-// Geometry shared by the staged kernels.  BWT / BHX: box width in texels / extra box rows beyond the tile height.
+// Geometry of the staged kernel.  BWT / BHX: box width in texels / extra box rows beyond the tile height.
 template <int C, int D, int ES, int BWT = MVSTER_BOX_BW, int BHX = MVSTER_BOX_BHX, int NBUFS = MVSTER_BOX_NBUF>
 struct BoxCfg {
     static constexpr int TB = C * ES;                                    // texel bytes: 16, 32 or 64
@@ -77,14 +74,19 @@ struct BoxCfg {
     // j ^ ROW_SWZ - a compile-time renaming, no extra instruction.
     static constexpr int ROW_SWZ = (ROW_BYTES >> 7) & (NSUB - 1);
     static constexpr int SWZ_PERIOD = TB == 64 ? 512 : (TB == 32 ? 256 : 128);  // bytes after which the pattern repeats
-    static constexpr int BAR_OFF = NBUF * BUF_BYTES;
-    static constexpr int BBOX_OFF = BAR_OFF + 64;
-    static constexpr int RT_OFF = BBOX_OFF + MVSTER_MAX_SRC_VIEWS * 16;
-    static constexpr int SMEM = RT_OFF + MVSTER_MAX_SRC_VIEWS * 48 + 1024;  // + slack for the 1024-byte alignment
+    static constexpr int BAR_OFF = NBUF * BUF_BYTES;                               // NBUF mbarriers
+    static constexpr int DESC_OFF = BAR_OFF + 64;                                  // float4 desc[views]: the plan
+    static constexpr int ORG_OFF = DESC_OFF + MVSTER_MAX_SRC_VIEWS * 16;           // int2 org[views]: box origin
+    static constexpr int WBOX_OFF = ORG_OFF + MVSTER_MAX_SRC_VIEWS * 8 + 8;        // int4 wbox[views][WARPS]
+    static constexpr int RT_OFF = WBOX_OFF + MVSTER_MAX_SRC_VIEWS * WARPS * 16;    // float rt[views][12], repacked
+    // no alignment slack: the dynamic shared-memory array is declared __align__(1024) (5 CTAs of the 32-byte-texel
+    // kernel fill the SM's 228 KB to within 2 KB - 1 KB more per CTA costs a whole CTA of occupancy)
+    static constexpr int SMEM = RT_OFF + MVSTER_MAX_SRC_VIEWS * 48;
     static_assert(DL % 2 == 0, "hypotheses are processed in packed pairs");
     static_assert(BUF_BYTES % SWZ_PERIOD == 0 && (TB == 16 || ROW_BYTES % 128 == 0), "buffers must not change the swizzle phase");
     static_assert(TB != 64 || (ROW_SWZ & 1) == 0, "64B swizzle: the row pitch must be a multiple of 256 bytes");
     static_assert(NBUF >= 1 && NBUF <= 8, "NBUF");
+    static_assert(MVSTER_MAX_SRC_VIEWS <= 32, "one lane of warp 0 plans one view");
 };
 
 __device__ __forceinline__ f32x2 add2_rm(f32x2 a, f32x2 b) {
@@ -109,17 +111,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
 }
 
 // Per-view constants of the sample-position arithmetic for one pixel; all of them carry the sign that makes the
@@ -152,12 +143,12 @@ __device__ __forceinline__ PixelView pixel_view(const float* rt_s, float fxp, fl
 // Positions of two hypotheses (h0, h1) of one pixel in one view: sx = (ax d + t0) / (az d + t2), same for sy, with the
 // reciprocal as MUFU.RCP + one Newton step (<= 1 ulp).  No clamp, no zero test: the bounding-box step rejects what
 // this produces for degenerate input.  Every caller of one kernel uses this same function, so they see identical bits.
-__device__ __forceinline__ void positions2(const PixelView& pv, f32x2 hh, f32x2& sx, f32x2& sy) {
+__device__ __forceinline__ void positions2(const PixelView& pv, f32x2 hh, f32x2& sx, f32x2& sy, f32x2& pz) {
     float nax, nay;
     unpack2(pv.naxy, nax, nay);
     const f32x2 npx = fma2(pack2(nax, nax), hh, pack2(pv.nt0, pv.nt0));
     const f32x2 npy = fma2(pack2(nay, nay), hh, pack2(pv.nt1, pv.nt1));
-    const f32x2 pz = fma2(pack2(pv.az, pv.az), hh, pack2(pv.t2, pv.t2));
+    pz = fma2(pack2(pv.az, pv.az), hh, pack2(pv.t2, pv.t2));
     float z0, z1;
     unpack2(pz, z0, z1);
     const f32x2 nr = pack2(rcp_approx(-z0), rcp_approx(-z1));            // -1/pz (approx)
@@ -182,12 +173,24 @@ __device__ __forceinline__ bool box_fits(const int4 bb, int& bx, int& by) {
 }
 
 // 8 channels (chunk c8 of the texel) of the upper (ROWSEL = 0) or lower (ROWSEL = 1) tap row.  aL = swizzled address of
-// the texel's logical 16-byte chunk 0 in the UPPER row.
+// the texel's logical 16-byte chunk 0 in the UPPER row.  Lanes with pred == false keep the previous contents of t (no
+// shared-memory access, and a quarter-warp without an active lane costs no wavefront).
+template <int OFF>
+__device__ __forceinline__ void lds_pairs_pred(uint32_t addr, f32x2& a, f32x2& b, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@p ld.shared.v2.b64 {%0,%1}, [%2+%3];\n\t}"
+        : "+l"(a), "+l"(b)
+        : "r"(addr), "n"(OFF), "r"((int)pred));
+}
 template <typename K, typename T, int ROWSEL>
 __device__ __forceinline__ void lds_tap(uint32_t aL, int c8, P8& t) {
     constexpr int RX = ROWSEL ? K::ROW_SWZ : 0;
     constexpr int OFF = ROWSEL ? K::ROW_BYTES : 0;
-    if constexpr (sizeof(T) == 4) {
+    if constexpr ((MVSTER_BOX_KO & 1) != 0) {
+        t.q[0] = pack2(__uint_as_float(aL), __uint_as_float(aL + OFF)); t.q[1] = t.q[0]; t.q[2] = t.q[0]; t.q[3] = t.q[0];
+    } else if constexpr (sizeof(T) == 4) {
         const uint32_t j0 = (uint32_t)((2 * c8) ^ RX) << 4, j1 = (uint32_t)((2 * c8 + 1) ^ RX) << 4;
         lds_pairs_at<OFF>(aL ^ j0, t.q[0], t.q[1]);
         lds_pairs_at<OFF>(aL ^ j1, t.q[2], t.q[3]);
@@ -201,91 +204,13 @@ __device__ __forceinline__ void lds_tap(uint32_t aL, int c8, P8& t) {
         t.q[3] = pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
     }
 }
-
-// ---- one view, staged path: cor[g][d] = group-wise correlation of the reference with the bilinear samples taken
-//      from the box at shared address `buf` whose origin is texel (bx, by) ------------------------------------------------
-template <typename K, int CPG, typename T>
-__device__ __forceinline__ void gather_view(const PixelView& pv, const f32x2 (&hh)[K::DL / 2], const f32x2* rf, uint32_t buf,
-                                            int bx, int by, float (&cor)[K::NCHUNK * (8 / CPG)][K::DL]) {
-    constexpr int DL = K::DL, NCHUNK = K::NCHUNK, TB = K::TB, ROW = K::ROW_BYTES, GPC = 8 / CPG;
-    constexpr uint32_t SWZ = K::SWZ;
-    const float kx = kFloorMagic - (float)bx, ky = kFloorMagic - (float)by;  // exact
-    // address of texel (rx, ry) = buf + ry * ROW + rx * TB with rx = bits(tx) - magic bits: fold the constants
-    const uint32_t bufk = buf - (uint32_t)kFloorMagicBits * (uint32_t)(ROW + TB);
-#pragma unroll
-    for (int k = 0; k < DL / 2; ++k) {
-        f32x2 sx, sy;
-        positions2(pv, hh[k], sx, sy);
-        const f32x2 tx = add2_rm(sx, pack2(kx, kx)), ty = add2_rm(sy, pack2(ky, ky));
-        const f32x2 flx = add2(tx, pack2(-kx, -kx)), fly = add2(ty, pack2(-ky, -ky));   // floor(s), exact
-        const f32x2 m1 = pack2(-1.0f, -1.0f), one = pack2(1.0f, 1.0f);
-        const f32x2 fx = fma2(flx, m1, sx), fy = fma2(fly, m1, sy);                     // s - floor(s), exact
-        const f32x2 gx = fma2(fx, m1, one), gy = fma2(fy, m1, one);
-        const f32x2 w00 = mul2(gx, gy), w01 = mul2(fx, gy), w10 = mul2(gx, fy), w11 = mul2(fx, fy);
-        float wa[2][4];
-        unpack2(w00, wa[0][0], wa[1][0]); unpack2(w01, wa[0][1], wa[1][1]);
-        unpack2(w10, wa[0][2], wa[1][2]); unpack2(w11, wa[0][3], wa[1][3]);
-        float txs[2], tys[2];
-        unpack2(tx, txs[0], txs[1]);
-        unpack2(ty, tys[0], tys[1]);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int d = 2 * k + j;
-            const uint32_t base = (uint32_t)__float_as_int(tys[j]) * (uint32_t)ROW +
-                                  ((uint32_t)__float_as_int(txs[j]) * (uint32_t)TB + bufk);
-            // hardware swizzle: 16-byte chunk index ^= address bits [8:7] (64B mode) / [7] (32B mode)
-            const uint32_t baseR = base + TB;
-            const uint32_t aL = base ^ ((base >> 3) & SWZ), aR = baseR ^ ((baseR >> 3) & SWZ);
-#pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                P8 t00, t01, t10, t11;
-                if constexpr ((MVSTER_BOX_KO & 1) != 0) {  // taps made of the addresses: no shared-memory traffic
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        t00.q[q] = pack2(__uint_as_float(aL), __uint_as_float(aR + q));
-                        t01.q[q] = pack2(__uint_as_float(aR), __uint_as_float(aL + q));
-                        t10.q[q] = t01.q[q]; t11.q[q] = t00.q[q];
-                    }
-                } else {
-                    lds_tap<K, T, 0>(aL, c, t00);
-                    lds_tap<K, T, 0>(aR, c, t01);
-                    lds_tap<K, T, 1>(aL, c, t10);
-                    lds_tap<K, T, 1>(aR, c, t11);
-                }
-                float cg[GPC];
-                if constexpr ((MVSTER_BOX_KO & 16) != 0) {  // keep the loads alive, drop the 20 packed + 4 scalar math ops
-                    const f32x2 xo = t00.q[0] ^ t01.q[1] ^ t10.q[2] ^ t11.q[3] ^ t00.q[1] ^ t01.q[2] ^ t10.q[3] ^ t11.q[0] ^
-                                     t00.q[2] ^ t01.q[3] ^ t10.q[0] ^ t11.q[1] ^ t00.q[3] ^ t01.q[0] ^ t10.q[1] ^ t11.q[2];
-                    float lo, hi;
-                    unpack2(xo, lo, hi);
-#pragma unroll
-                    for (int g = 0; g < GPC; ++g) cg[g] = (g & 1) ? hi * wa[j][g & 3] : lo * wa[j][g & 3];
-                } else {
-                    blend_correlate<CPG>(t00, t01, t10, t11, wa[j][0], wa[j][1], wa[j][2], wa[j][3], rf + c * 4, cg);
-                }
-#pragma unroll
-                for (int g = 0; g < GPC; ++g) cor[c * GPC + g][d] = cg[g];
-            }
-        }
-    }
-}
-
-// Predicated variant: lanes with pred == false keep the previous contents of t (no shared-memory access, and a
-// quarter-warp without an active lane costs no wavefront).
-template <int OFF>
-__device__ __forceinline__ void lds_pairs_pred(uint32_t addr, f32x2& a, f32x2& b, bool pred) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@p ld.shared.v2.b64 {%0,%1}, [%2+%3];\n\t}"
-        : "+l"(a), "+l"(b)
-        : "r"(addr), "n"(OFF), "r"((int)pred));
-}
 template <typename K, typename T, int ROWSEL>
 __device__ __forceinline__ void lds_tap_pred(uint32_t aL, int c8, P8& t, bool pred) {
     constexpr int RX = ROWSEL ? K::ROW_SWZ : 0;
     constexpr int OFF = ROWSEL ? K::ROW_BYTES : 0;
-    if constexpr (sizeof(T) == 4) {
+    if constexpr ((MVSTER_BOX_KO & 1) != 0) {
+        if (pred) { t.q[0] = pack2(__uint_as_float(aL), __uint_as_float(aL + OFF)); t.q[2] = t.q[0]; }
+    } else if constexpr (sizeof(T) == 4) {
         const uint32_t j0 = (uint32_t)((2 * c8) ^ RX) << 4, j1 = (uint32_t)((2 * c8 + 1) ^ RX) << 4;
         lds_pairs_pred<OFF>(aL ^ j0, t.q[0], t.q[1], pred);
         lds_pairs_pred<OFF>(aL ^ j1, t.q[2], t.q[3], pred);
@@ -295,52 +220,54 @@ __device__ __forceinline__ void lds_tap_pred(uint32_t aL, int c8, P8& t, bool pr
 }
 
 // ---- one view, staged path with texel-column slots -------------------------------------------------------------------
-// The D hypotheses of a pixel walk along the epipolar line in sub-texel to ~1-texel steps (profiles/r02: 7.7 distinct
-// texels behind the 16 taps of a stage-4 pixel and view), and the shared-memory data pipe is the busiest unit of this
-// kernel.  A lane therefore keeps two texel COLUMNS (upper and lower tap row each) in registers and addresses them by
-// the parity of the column index relative to the first hypothesis' cell: a sample whose cell is k columns away from
-// sample 0 uses the slot of parity k for its left taps and the other one for its right taps; only a slot whose
-// column changed is loaded again (predicated LDS - no branch, no data movement between registers; the bilinear x
-// weights are swapped instead).  Because the parity is taken relative to the lane's own first cell, neighbouring lanes
-// reload the same slot at the same hypothesis, so whole quarter-warps skip the access together.  A change of the tap
-// row (rare: epipolar lines are close to horizontal or the step is sub-texel) reloads both slots.
+// The D hypotheses of a pixel walk along the epipolar line in sub-texel to ~1-texel steps (stage 4 of the benchmark:
+// 0.25 / 0.5 / 0.75 / 1.0 texels per hypothesis for the four source views, 3.85 distinct texel columns on average
+// behind the 8 columns of a pixel's taps in one view; the tap row changes for < 4 % of the pixels), and the
+// shared-memory data pipe is one of the two busiest units of this kernel.  A lane therefore keeps two texel COLUMNS
+// (upper and lower tap row each) in registers and addresses them by the parity of the column index relative to the
+// first hypothesis' cell: a sample whose cell is k columns away from sample 0 uses the slot of parity k for its left
+// taps and the other one for its right taps; only a slot whose texel address changed is loaded again (predicated LDS
+// - no branch, no data movement between registers; the bilinear x weights are swapped instead).
+// cor2[g][k] = correlation of group g for the hypothesis pair k, packed.
+// (kx, ky) = floor magic - box origin; bufk = shared address of the box - magic bits * (ROW + TB): both from the plan.
 template <typename K, int CPG, typename T>
 __device__ __forceinline__ void gather_view_slots(const PixelView& pv, const f32x2 (&hh)[K::DL / 2], const f32x2* rf,
-                                                  uint32_t buf, int bx, int by, float (&cor)[K::NCHUNK * (8 / CPG)][K::DL]) {
+                                                  float kx, float ky, uint32_t bufk,
+                                                  f32x2 (&cor2)[K::NCHUNK * (8 / CPG)][K::DL / 2]) {
     constexpr int DL = K::DL, NCHUNK = K::NCHUNK, TB = K::TB, ROW = K::ROW_BYTES, GPC = 8 / CPG;
     constexpr uint32_t SWZ = K::SWZ;
-    const float kx = kFloorMagic - (float)bx, ky = kFloorMagic - (float)by;  // exact
-    const uint32_t bufk = buf - (uint32_t)kFloorMagicBits * (uint32_t)(ROW + TB);
     float fxs[DL], fys[DL];
-    int txi[DL], tyi[DL];
+    uint32_t xb[DL], ua[DL];   // column byte offset (texel x * TB) and unswizzled address of the left texel, upper row
 #pragma unroll
     for (int k = 0; k < DL / 2; ++k) {
-        f32x2 sx, sy;
-        positions2(pv, hh[k], sx, sy);
+        f32x2 sx, sy, pz;
+        positions2(pv, hh[k], sx, sy, pz);
         const f32x2 tx = add2_rm(sx, pack2(kx, kx)), ty = add2_rm(sy, pack2(ky, ky));
         const f32x2 flx = add2(tx, pack2(-kx, -kx)), fly = add2(ty, pack2(-ky, -ky));   // floor(s), exact
         const f32x2 m1 = pack2(-1.0f, -1.0f);
         const f32x2 fx = fma2(flx, m1, sx), fy = fma2(fly, m1, sy);                     // s - floor(s), exact
         unpack2(fx, fxs[2 * k], fxs[2 * k + 1]);
         unpack2(fy, fys[2 * k], fys[2 * k + 1]);
-        float a0, a1;
-        unpack2(tx, a0, a1); txi[2 * k] = __float_as_int(a0); txi[2 * k + 1] = __float_as_int(a1);
-        unpack2(ty, a0, a1); tyi[2 * k] = __float_as_int(a0); tyi[2 * k + 1] = __float_as_int(a1);
+        float a0, a1, b0, b1;
+        unpack2(tx, a0, a1);
+        unpack2(ty, b0, b1);
+        xb[2 * k] = (uint32_t)__float_as_int(a0) * (uint32_t)TB;
+        xb[2 * k + 1] = (uint32_t)__float_as_int(a1) * (uint32_t)TB;
+        ua[2 * k] = (uint32_t)__float_as_int(b0) * (uint32_t)ROW + (xb[2 * k] + bufk);
+        ua[2 * k + 1] = (uint32_t)__float_as_int(b1) * (uint32_t)ROW + (xb[2 * k + 1] + bufk);
     }
-    // column slots: S[a][row][chunk]; slot a holds the column of relative index c_a (parity a)
+    // column slots: S[a][row][chunk]; slot a holds the column whose index relative to sample 0's cell has parity a
     P8 S[2][2][NCHUNK];
-    const uint32_t col0 = (uint32_t)txi[0] * (uint32_t)TB + bufk;   // byte offset of the first sample's left column
-    int pc0 = 0, pc1 = 0;
+    float cor[NCHUNK * GPC][DL];
+    uint32_t pb0 = 0, pb1 = 0;
 #pragma unroll
     for (int d = 0; d < DL; ++d) {
-        const int kc = txi[d] - txi[0];                 // cell column relative to sample 0 (any sign)
-        const int c0 = (kc + 1) & ~1, c1 = kc | 1;      // the even / odd one of {kc, kc + 1}
-        const bool rowchg = d > 0 && tyi[d] != tyi[d - 1];
-        const bool need0 = d == 0 || rowchg || c0 != pc0;
-        const bool need1 = d == 0 || rowchg || c1 != pc1;
-        pc0 = c0; pc1 = c1;
-        const uint32_t rowa = (uint32_t)tyi[d] * (uint32_t)ROW + col0;
-        const uint32_t b0 = rowa + (uint32_t)(c0 * TB), b1 = rowa + (uint32_t)(c1 * TB);
+        // relative column parity of this sample's cell: its left texel sits in slot `odd`, its right one in the other
+        const uint32_t o = (xb[d] ^ xb[0]) & (uint32_t)TB;
+        const uint32_t b0 = ua[d] + o, b1 = ua[d] + (uint32_t)TB - o;   // unswizzled addresses of the slot texels
+        const bool need0 = d == 0 || b0 != pb0, need1 = d == 0 || b1 != pb1;
+        pb0 = b0; pb1 = b1;
+        // hardware swizzle: 16-byte chunk index ^= address bits [8:7] (64B mode) / [7] (32B mode)
         const uint32_t a0 = b0 ^ ((b0 >> 3) & SWZ), a1 = b1 ^ ((b1 >> 3) & SWZ);
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
@@ -352,33 +279,50 @@ __device__ __forceinline__ void gather_view_slots(const PixelView& pv, const f32
                 lds_tap_pred<K, T, 0>(a1, c, S[1][0][c], need1); lds_tap_pred<K, T, 1>(a1, c, S[1][1][c], need1);
             }
         }
-        // left taps sit in the slot of parity kc: swap the x weights instead of the data
-        const bool odd = (kc & 1) != 0;
+        // slot weights: the left tap's weight goes to the slot that holds the left texel
+        const bool odd = o != 0;
         const float gxd = 1.0f - fxs[d], gyd = 1.0f - fys[d];
         const float w0 = odd ? fxs[d] : gxd, w1 = odd ? gxd : fxs[d];
+        float wt0, wt1, wb0, wb1;
+        unpack2(mul2(pack2(w0, w1), pack2(gyd, gyd)), wt0, wt1);
+        unpack2(mul2(pack2(w0, w1), pack2(fys[d], fys[d])), wb0, wb1);
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
             float cg[GPC];
-            blend_correlate<CPG>(S[0][0][c], S[1][0][c], S[0][1][c], S[1][1][c], w0 * gyd, w1 * gyd, w0 * fys[d], w1 * fys[d],
-                                 rf + c * 4, cg);
+            if constexpr ((MVSTER_BOX_KO & 4) != 0) {  // keep the loads alive, drop the packed math
+                const f32x2 xo = S[0][0][c].q[0] ^ S[1][0][c].q[1] ^ S[0][1][c].q[2] ^ S[1][1][c].q[3] ^ S[0][0][c].q[1] ^
+                                 S[1][0][c].q[2] ^ S[0][1][c].q[3] ^ S[1][1][c].q[0] ^ S[0][0][c].q[2] ^ S[1][0][c].q[3] ^
+                                 S[0][1][c].q[0] ^ S[1][1][c].q[1] ^ S[0][0][c].q[3] ^ S[1][0][c].q[0] ^ S[0][1][c].q[1] ^
+                                 S[1][1][c].q[2];
+                float lo, hi;
+                unpack2(xo, lo, hi);
+#pragma unroll
+                for (int g = 0; g < GPC; ++g) cg[g] = (g & 1) ? hi * wt0 + wb1 : lo * wt1 + wb0;
+            } else
+            blend_correlate<CPG>(S[0][0][c], S[1][0][c], S[0][1][c], S[1][1][c], wt0, wt1, wb0, wb1, rf + c * 4, cg);
 #pragma unroll
             for (int g = 0; g < GPC; ++g) cor[c * GPC + g][d] = cg[g];
         }
     }
+#pragma unroll
+    for (int g = 0; g < NCHUNK * GPC; ++g)
+#pragma unroll
+        for (int k = 0; k < DL / 2; ++k) cor2[g][k] = pack2(cor[g][2 * k], cor[g][2 * k + 1]);
 }
 
 // ---- one view, exact path for footprints larger than the box (or degenerate positions): direct gather from global
 //      memory with the reference's clamp / zero test / per-tap bounds weights -----------------------------------------
 template <typename K, int CPG, typename T>
 __device__ __forceinline__ void direct_view(const float* rt12, const void* src_b, int Hs, int Ws, float fxp, float fyp,
-                                            const f32x2 (&hh)[K::DL / 2], const f32x2* rf,
-                                            float (&cor)[K::NCHUNK * (8 / CPG)][K::DL]) {
+                                         const f32x2 (&hh)[K::DL / 2], const f32x2* rf,
+                                         f32x2 (&cor2)[K::NCHUNK * (8 / CPG)][K::DL / 2]) {
     constexpr int DL = K::DL, NCHUNK = K::NCHUNK, TB = K::TB, GPC = 8 / CPG;
     const Homography h = load_homography(rt12);
     const float ax = fmaf(h.r00, fxp, fmaf(h.r01, fyp, h.r02));
     const float ay = fmaf(h.r10, fxp, fmaf(h.r11, fyp, h.r12));
     const float az = fmaf(h.r20, fxp, fmaf(h.r21, fyp, h.r22));
     const char* srcp = reinterpret_cast<const char*>(src_b);
+    float cor[NCHUNK * GPC][DL];
 #pragma unroll
     for (int d = 0; d < DL; ++d) {
         float h0, h1;
@@ -397,43 +341,54 @@ __device__ __forceinline__ void direct_view(const float* rt12, const void* src_b
             for (int g = 0; g < GPC; ++g) cor[c * GPC + g][d] = cg[g];
         }
     }
+#pragma unroll
+    for (int g = 0; g < NCHUNK * GPC; ++g)
+#pragma unroll
+        for (int k = 0; k < DL / 2; ++k) cor2[g][k] = pack2(cor[g][2 * k], cor[g][2 * k + 1]);
 }
 
 // ---- epipolar attention of one view and its contribution to the aggregate ---------------------------------------------
 // score[d] = sum over all G groups (reference cor_feat.sum(1), :1083); w = softmax over D of score / attn_temp, divided
-// by sqrt(C); max and sum cross the LD hypothesis lanes of the pixel.  Returns the weights in w[] (for `weights`).
+// by sqrt(C); max and sum cross the LD hypothesis lanes of the pixel.  Everything is packed across hypothesis pairs.
+// Returns the weights in w2[] (for `weights`).
 template <typename K, int GPL>
-__device__ __forceinline__ void attend_accumulate(const float (&cor)[GPL][K::DL], float score_scale, float inv_sqrt_c,
-                                                  float (&acc)[GPL][K::DL], float (&wsum)[K::DL], float (&w)[K::DL]) {
-    constexpr int DL = K::DL, LD = K::LD;
-    float score[DL];
+__device__ __forceinline__ void attend_accumulate(const f32x2 (&cor2)[GPL][K::DL / 2], float score_scale, float inv_sqrt_c,
+                                                  f32x2 (&acc2)[GPL][K::DL / 2], f32x2 (&wsum2)[K::DL / 2],
+                                                  f32x2 (&w2)[K::DL / 2]) {
+    constexpr int NP = K::DL / 2, LD = K::LD;
+    f32x2 s2[NP];
+    float mx;
 #pragma unroll
-    for (int d = 0; d < DL; ++d) {
-        float s = cor[0][d];
+    for (int k = 0; k < NP; ++k) {
+        f32x2 s = cor2[0][k];
 #pragma unroll
-        for (int g = 1; g < GPL; ++g) s += cor[g][d];
-        score[d] = s;
+        for (int g = 1; g < GPL; ++g) s = add2(s, cor2[g][k]);
+        s2[k] = s;
+        float lo, hi;
+        unpack2(s, lo, hi);
+        mx = k == 0 ? fmaxf(lo, hi) : fmaxf(mx, fmaxf(lo, hi));
     }
-    float mx = score[0];
-#pragma unroll
-    for (int d = 1; d < DL; ++d) mx = fmaxf(mx, score[d]);
 #pragma unroll
     for (int m = 1; m < LD; m <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    const float nmxs = -mx * score_scale;
     float es = 0.0f;
 #pragma unroll
-    for (int d = 0; d < DL; ++d) {
-        w[d] = ex2_approx((score[d] - mx) * score_scale);
-        es += w[d];
+    for (int k = 0; k < NP; ++k) {
+        float lo, hi;
+        unpack2(fma2(s2[k], pack2(score_scale, score_scale), pack2(nmxs, nmxs)), lo, hi);   // <= 0
+        lo = ex2_approx(lo); hi = ex2_approx(hi);
+        w2[k] = pack2(lo, hi);
+        es += lo + hi;
     }
 #pragma unroll
     for (int m = 1; m < LD; m <<= 1) es += __shfl_xor_sync(0xffffffffu, es, m);
-    const float norm = __fdividef(inv_sqrt_c, es);
+    const float norm = inv_sqrt_c * rcp_approx(es);    // es in [1, D]: MUFU.RCP is within 1 ulp there
 #pragma unroll
-    for (int d = 0; d < DL; ++d) {
-        w[d] *= norm;
-        wsum[d] += w[d];
+    for (int k = 0; k < NP; ++k) {
+        w2[k] = mul2(w2[k], pack2(norm, norm));
+        wsum2[k] = add2(wsum2[k], w2[k]);
 #pragma unroll
-        for (int g = 0; g < GPL; ++g) acc[g][d] = fmaf(w[d], cor[g][d], acc[g][d]);
+        for (int g = 0; g < GPL; ++g) acc2[g][k] = fma2(w2[k], cor2[g][k], acc2[g][k]);
     }
 }
 
@@ -455,17 +410,19 @@ template <int C, int CPG, int D, typename T>
 __global__ void __launch_bounds__(BoxCfg<C, D, (int)sizeof(T)>::WARPS * 32, BoxCfg<C, D, (int)sizeof(T)>::MINB)
     epi_fwd_box_kernel(const __grid_constant__ EpiFwdParams p) {
     using K = BoxCfg<C, D, (int)sizeof(T)>;
-    constexpr int DL = K::DL, LD = K::LD, TB = K::TB, NBUF = K::NBUF;
+    constexpr int DL = K::DL, LD = K::LD, TB = K::TB, NBUF = K::NBUF, NP = DL / 2, WARPS = K::WARPS;
     constexpr int G = C / CPG, GPL = G;              // a lane owns all channels = all groups
-    constexpr int NT = K::WARPS * 32;
+    constexpr int NT = WARPS * 32;
     static_assert(8 % CPG == 0, "a chunk of 8 channels must hold whole groups");
 
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    unsigned char* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+    extern __shared__ __align__(1024) unsigned char smem_box[];
+    const uint32_t smem_base = smem_u32(smem_box);
+    unsigned char* sm = smem_box;
     const uint32_t bars = smem_base + K::BAR_OFF;
-    int* bbox = reinterpret_cast<int*>(sm + K::BBOX_OFF);      // [view][4]: min x, min y, max x, max y (magic-offset bits)
-    float* rt_s = reinterpret_cast<float*>(sm + K::RT_OFF);    // [view][12], repacked (see pixel_view)
+    float4* desc = reinterpret_cast<float4*>(sm + K::DESC_OFF);  // [view] {kx, ky, bufk bits, staged? bits}
+    int2* org = reinterpret_cast<int2*>(sm + K::ORG_OFF);        // [view] box origin in texels
+    int4* wbox = reinterpret_cast<int4*>(sm + K::WBOX_OFF);      // [view][warp] {min x, min y, max x, max y} magic bits
+    float* rt_s = reinterpret_cast<float*>(sm + K::RT_OFF);      // [view][12], repacked (see pixel_view)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pix = lane / LD, dl = lane % LD;
@@ -474,10 +431,6 @@ __global__ void __launch_bounds__(BoxCfg<C, D, (int)sizeof(T)>::WARPS * 32, BoxC
     {
         const float* rtg = p.rt + (size_t)b * Nsrc * 12;
         for (int i = tid; i < Nsrc * 12; i += NT) rt_s[i] = repack_rt(rtg + (i / 12) * 12, i % 12);
-        if (tid < Nsrc) {
-            bbox[tid * 4 + 0] = INT_MAX; bbox[tid * 4 + 1] = INT_MAX;
-            bbox[tid * 4 + 2] = INT_MIN; bbox[tid * 4 + 3] = INT_MIN;
-        }
         if (tid == 0) {
 #pragma unroll
             for (int i = 0; i < NBUF; ++i) mbar_init(bars + 8u * i, 1);
@@ -493,113 +446,156 @@ __global__ void __launch_bounds__(BoxCfg<C, D, (int)sizeof(T)>::WARPS * 32, BoxC
     const size_t pix_off = (size_t)y * p.W + x;
     const float fxp = (float)x, fyp = (float)y;
 
-    f32x2 hh[DL / 2];
+    f32x2 hh[NP];
+    f32x2 hext;   // this lane's extreme hypotheses
     {
         float hyp[DL];
+        const float* hp = p.hypo + ((size_t)b * D + dl * DL) * plane + pix_off;
 #pragma unroll
-        for (int d = 0; d < DL; ++d) hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + dl * DL + d) * plane + pix_off);
+        for (int d = 0; d < DL; ++d) hyp[d] = ldg_stream(hp + d * plane);
+        float hlo = hyp[0], hhi = hyp[0];
 #pragma unroll
-        for (int k = 0; k < DL / 2; ++k) hh[k] = pack2(hyp[2 * k], hyp[2 * k + 1]);
+        for (int d = 1; d < DL; ++d) { hlo = min_nan(hlo, hyp[d]); hhi = max_nan(hhi, hyp[d]); }
+        hext = pack2(hlo, hhi);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) hh[k] = pack2(hyp[2 * k], hyp[2 * k + 1]);
     }
     f32x2 rf[C / 2];
     load_ref<C, CPG, T>(p.ref, (size_t)b * plane + pix_off, rf);  // in flight across phase A
-    __syncthreads();  // rt_s, bbox slots, mbarriers
+    __syncthreads();  // rt_s, mbarriers
 
-    // ---- phase A: bounding box of every view's sample positions ------------------------------------------------
+    // ---- phase A: bounding box of every view's sample positions --------------------------------------------------
+    // Along one pixel's epipolar line the position is a Moebius function of the depth, monotone between the extreme
+    // hypotheses unless z changes sign in between - which poisons the box with a NaN (no fit -> exact direct path).
 #pragma unroll 1
     for (int v = 0; v < Nsrc; ++v) {
         const PixelView pv = pixel_view(rt_s + v * 12, fxp, fyp);
-        float lox, hix, loy, hiy;
-#pragma unroll
-        for (int k = 0; k < DL / 2; ++k) {
-            f32x2 sx, sy;
-            positions2(pv, hh[k], sx, sy);
-            float x0, x1, y0, y1;
-            unpack2(sx, x0, x1);
-            unpack2(sy, y0, y1);
-            if (k == 0) {
-                lox = min_nan(x0, x1); hix = max_nan(x0, x1);
-                loy = min_nan(y0, y1); hiy = max_nan(y0, y1);
-            } else {
-                lox = min_nan(lox, min_nan(x0, x1)); hix = max_nan(hix, max_nan(x0, x1));
-                loy = min_nan(loy, min_nan(y0, y1)); hiy = max_nan(hiy, max_nan(y0, y1));
-            }
-        }
-        // a NaN anywhere makes hix / hiy NaN -> 0x7fffffff after the add -> the box cannot fit.  ptxas turns a
-        // warp-uniform-address shared atomic into REDUX + one ATOMS by an elected lane.
-        int* slot = bbox + v * 4;
-        atomicMin(slot + 0, __float_as_int(__fadd_rd(lox, kFloorMagic)));
-        atomicMin(slot + 1, __float_as_int(__fadd_rd(loy, kFloorMagic)));
-        atomicMax(slot + 2, __float_as_int(__fadd_rd(hix, kFloorMagic)));
-        atomicMax(slot + 3, __float_as_int(__fadd_rd(hiy, kFloorMagic)));
+        f32x2 sx, sy, pz;
+        positions2(pv, hext, sx, sy, pz);
+        float x0, x1, y0, y1, z0, z1;
+        unpack2(sx, x0, x1);
+        unpack2(sy, y0, y1);
+        unpack2(pz, z0, z1);
+        x1 = (z0 * z1 > 0.0f) ? x1 : __int_as_float(0x7fffffff);
+        // Every computed position is within 2^-21 (relative) of the exact Moebius function of the fp32 constants
+        // (single-rounding FMAs, reciprocal <= 1 ulp), so the positions of the hypotheses in between stay inside
+        // [min, max] widened by 2^-19 of the larger magnitude.  A NaN anywhere makes hix / hiy NaN -> 0x7fffffff
+        // after the add -> the box cannot fit.
+        constexpr float kRel = 1.9073486328125e-06f;  // 2^-19
+        const float mx = max_nan(fabsf(x0), fabsf(x1)) * kRel, my = max_nan(fabsf(y0), fabsf(y1)) * kRel;
+        const int lox = __float_as_int(__fadd_rd(min_nan(x0, x1) - mx, kFloorMagic));
+        const int loy = __float_as_int(__fadd_rd(min_nan(y0, y1) - my, kFloorMagic));
+        const int hix = __float_as_int(__fadd_rd(max_nan(x0, x1) + mx, kFloorMagic));
+        const int hiy = __float_as_int(__fadd_rd(max_nan(y0, y1) + my, kFloorMagic));
+        int4 wb;
+        wb.x = __reduce_min_sync(0xffffffffu, lox);
+        wb.y = __reduce_min_sync(0xffffffffu, loy);
+        wb.z = __reduce_max_sync(0xffffffffu, hix);
+        wb.w = __reduce_max_sync(0xffffffffu, hiy);
+        if (lane == 0) wbox[v * WARPS + warp] = wb;
     }
     __syncthreads();
 
-    auto request = [&](int v) {  // one thread
-        int bx, by;
-        if (!(MVSTER_BOX_KO & 2) && box_fits<K>(*reinterpret_cast<const int4*>(bbox + v * 4), bx, by)) {
-            const uint32_t bar = bars + 8u * (v % NBUF);
+    // ---- the plan: one lane of warp 0 per view combines the warp boxes, publishes the descriptor and requests the
+    //      box (or, when it does not fit, completes the view's barrier by hand).  The other warps pick the descriptor
+    //      up behind the mbarrier (arrive = release, wait = acquire).
+    auto request = [&](int v, bool fit, int bx, int by) {  // one thread
+        const uint32_t bar = bars + 8u * (v % NBUF);
+        if (fit && !(MVSTER_BOX_KO & 2)) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of a recycled buffer
             mbar_expect_tx(bar, (uint32_t)K::BUF_BYTES);
             tma_load_4d(smem_base + (uint32_t)K::BUF_BYTES * (v % NBUF), &p.tmap[v], bar, 0, bx, by, b);
+        } else {
+            mbar_arrive(bar);
         }
     };
-    if (tid == 0) {
-        for (int v = 0; v < Nsrc && v < NBUF; ++v) request(v);
+    if (warp == 0 && lane < Nsrc) {
+        const int v = lane;
+        int4 bb = wbox[v * WARPS];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) {
+            const int4 o = wbox[v * WARPS + w];
+            bb.x = min(bb.x, o.x); bb.y = min(bb.y, o.y); bb.z = max(bb.z, o.z); bb.w = max(bb.w, o.w);
+        }
+        int bx, by;
+        const bool fit = box_fits<K>(bb, bx, by);
+        const uint32_t buf = smem_base + (uint32_t)K::BUF_BYTES * (v % NBUF);
+        // address of texel (rx, ry) = buf + ry * ROW + rx * TB with rx = bits(tx) - magic bits: fold the constants
+        const uint32_t bufk = buf - (uint32_t)kFloorMagicBits * (uint32_t)(K::ROW_BYTES + TB);
+        desc[v] = make_float4(kFloorMagic - (float)bx, kFloorMagic - (float)by, __uint_as_float(bufk),
+                              __int_as_float(fit ? 1 : 0));
+        org[v] = make_int2(bx, by);
+        if (v < NBUF) request(v, fit, bx, by);
     }
 
-    float acc[GPL][DL], wsum[DL];
+    f32x2 acc2[GPL][NP], wsum2[NP];
 #pragma unroll
-    for (int d = 0; d < DL; ++d) {
-        wsum[d] = 1e-8f;  // reference :1037
+    for (int k = 0; k < NP; ++k) {
+        wsum2[k] = pack2(1e-8f, 1e-8f);  // reference :1037
 #pragma unroll
-        for (int g = 0; g < GPL; ++g) acc[g][d] = 0.0f;
+        for (int g = 0; g < GPL; ++g) acc2[g][k] = pack2(0.0f, 0.0f);
     }
 
     // ---- phase B: gather, correlate, attend, accumulate ------------------------------------------------------
-    uint32_t phase_bits = 0;  // bit k: parity of the next completion of mbarrier k (uniform across the CTA)
 #pragma unroll 1
     for (int v = 0; v < Nsrc; ++v) {
-        int bx, by;
-        const bool fit = box_fits<K>(*reinterpret_cast<const int4*>(bbox + v * 4), bx, by);
-        float cor[GPL][DL];
-        if (fit) {
+        mbar_wait(bars + 8u * (v % NBUF), (uint32_t)(v / NBUF) & 1u);  // the slot's (v / NBUF)-th completion
+        const float4 dsc = desc[v];
+        f32x2 cor2[GPL][NP];
+        if (__float_as_int(dsc.w) != 0) {
             const PixelView pv = pixel_view(rt_s + v * 12, fxp, fyp);
-            const int slot = v % NBUF;
-            if (!(MVSTER_BOX_KO & 2)) mbar_wait(bars + 8u * slot, (phase_bits >> slot) & 1u);
-            phase_bits ^= 1u << slot;
-            if constexpr (MVSTER_BOX_SLOTS != 0)
-                gather_view_slots<K, CPG, T>(pv, hh, rf, smem_base + (uint32_t)K::BUF_BYTES * slot, bx, by, cor);
-            else
-                gather_view<K, CPG, T>(pv, hh, rf, smem_base + (uint32_t)K::BUF_BYTES * slot, bx, by, cor);
+            gather_view_slots<K, CPG, T>(pv, hh, rf, dsc.x, dsc.y, __float_as_uint(dsc.z), cor2);
         } else {
             direct_view<K, CPG, T>(p.rt + ((size_t)b * Nsrc + v) * 12,
                                    reinterpret_cast<const char*>(p.src[v]) + (size_t)b * p.Hs * p.Ws * TB, p.Hs, p.Ws, fxp,
-                                   fyp, hh, rf, cor);
+                                   fyp, hh, rf, cor2);
         }
-        float w[DL];
-        attend_accumulate<K, GPL>(cor, p.score_scale, p.inv_sqrt_c, acc, wsum, w);
+        f32x2 w2[NP];
+        attend_accumulate<K, GPL>(cor2, p.score_scale, p.inv_sqrt_c, acc2, wsum2, w2);
         if (p.weights != nullptr && live) {
+            float* wp = p.weights + (((size_t)b * Nsrc + v) * D + dl * DL) * plane + pix_off;
 #pragma unroll
-            for (int d = 0; d < DL; ++d)
-                p.weights[(((size_t)b * Nsrc + v) * D + dl * DL + d) * plane + pix_off] = w[d];
+            for (int k = 0; k < NP; ++k) {
+                float lo, hi;
+                unpack2(w2[k], lo, hi);
+                wp[(2 * k) * plane] = lo;
+                wp[(2 * k + 1) * plane] = hi;
+            }
         }
         if (v + NBUF < Nsrc) {  // more views than buffers: recycle this view's buffer once every warp has left it
             __syncthreads();
-            if (tid == 0) request(v + NBUF);
+            if (tid == 0) {
+                const int2 o = org[v + NBUF];
+                request(v + NBUF, __float_as_int(desc[v + NBUF].w) != 0, o.x, o.y);
+            }
         }
     }
 
     if (!live) return;
+    float inv[DL];
 #pragma unroll
-    for (int d = 0; d < DL; ++d) {
-        const float inv = __frcp_rn(wsum[d]);
-        const int dd = dl * DL + d;
+    for (int k = 0; k < NP; ++k) {
+        float lo, hi;
+        unpack2(wsum2[k], lo, hi);
+        inv[2 * k] = fast_rcp(lo);      // wsum >= 1e-8, far from the denormal range: MUFU.RCP + Newton is <= 1 ulp
+        inv[2 * k + 1] = fast_rcp(hi);
+        if (p.wsum != nullptr) {
+            float* ws = p.wsum + ((size_t)b * D + dl * DL + 2 * k) * plane + pix_off;
+            ws[0] = lo;
+            ws[plane] = hi;
+        }
+    }
+    float* op = p.out + ((size_t)b * G * D + dl * DL) * plane + pix_off;
 #pragma unroll
-        for (int g = 0; g < GPL; ++g)
-            if (!(MVSTER_BOX_KO & 8) || acc[g][d] * inv == 1234.5678f)
-                stg_stream(p.out + (((size_t)b * G + g) * D + dd) * plane + pix_off, acc[g][d] * inv);
-        if (p.wsum != nullptr) p.wsum[((size_t)b * D + dd) * plane + pix_off] = wsum[d];
+    for (int g = 0; g < GPL; ++g) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            float lo, hi;
+            unpack2(acc2[g][k], lo, hi);
+            stg_stream(op + (2 * k) * plane, lo * inv[2 * k]);
+            stg_stream(op + (2 * k + 1) * plane, hi * inv[2 * k + 1]);
+        }
+        op += (size_t)D * plane;
     }
 }
 
