@@ -57,7 +57,7 @@ def parse_args():
                     help="skip the secondary whole-network (FPN4 + reg2d + hot path) measurement on rank 0 at N=1")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not pin each rank (N > 1) to the CPUs local to its GPU before allocating pinned buffers")
-    ap.add_argument("--cpu-scenes", type=int, default=10, help="timed scenes of the CPU baseline sample")
+    ap.add_argument("--cpu-scenes", type=int, default=8, help="timed scenes of the CPU baseline sample")
     return ap.parse_args()
 
 
@@ -147,10 +147,14 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # synthetic workload
 # ---------------------------------------------------------------------------------------------------------------------
-def gt_inverse_depth(batch, h, w, seed, device):
-    """Smooth synthetic ground-truth surface (inverse depth) per scene: what a trained regnet would converge to."""
-    maps = [1.0 / syn.smooth_depth_map(h, w, seed + i, lo=560.0, hi=800.0) for i in range(batch)]
-    return torch.from_numpy(np.stack(maps).astype(np.float32)).to(device)
+def scene_seed(rank: int, index: int) -> int:
+    """Seed of scene ``index`` of rank ``rank``'s batch - the ONE place both arms take their scenes from."""
+    return 1234 + 1000 * rank + index
+
+
+def scene_gt_inverse_depth(seed, h, w):
+    """Smooth synthetic ground-truth surface (inverse depth) of one scene: what a trained regnet would converge to."""
+    return torch.from_numpy((1.0 / syn.smooth_depth_map(h, w, seed, lo=560.0, hi=800.0)).astype(np.float32))[None]
 
 
 def tracking_logits(hypo, inv_gt, noise):
@@ -162,22 +166,39 @@ def tracking_logits(hypo, inv_gt, noise):
     return -4.0 * (inv - inv_gt[:, None]).abs() / itv + noise
 
 
-def fill_plan(plan, seed: int):
-    g = torch.Generator(device=plan.device)
-    g.manual_seed(seed)
-    for s in range(plan.nstage):
-        (h, w), c = plan.shapes[s], plan.channels[s]
-        for v in range(plan.N):
-            x = torch.randn((plan.B, c, h, w), device=plan.device, generator=g) * 0.5
-            x = torch.nn.functional.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False) * 1.7
-            plan.features[s][v].copy_(x.permute(0, 2, 3, 1))
-            del x
-        plan.proj[s].copy_(torch.from_numpy(syn.proj_matrices(plan.B, plan.N, plan.h0, plan.w0, s,
-                                                              per_batch_jitter=0.02)))
-    plan.depth_values.copy_(torch.from_numpy(syn.depth_values(plan.B)))
-    # one untimed set-up pass computes the stand-in regnet outputs for the hypotheses the cascade really visits
-    gts = [gt_inverse_depth(plan.B, h, w, seed, plan.device) for (h, w) in plan.shapes]
-    noises = [torch.randn(plan.logits[s].shape, device=plan.device, generator=g) * 0.5 for s in range(plan.nstage)]
+def make_scene(seed, nviews, h0, w0, jitter_index=0):
+    """One synthetic scene (B=1, CPU tensors), used by BOTH arms: FPN-like feature maps ``features[s][v]`` [1,C,H,W]
+    (N(0, 0.5^2), 3x3 box-smoothed - SURVEY 8d), cameras ``projs[s]`` [1,N,2,4,4] (Appendix B rig; ``jitter_index``
+    varies the baseline by 2 % per scene of a batch), the depth range, the ground-truth inverse depth and the logit
+    noise per stage."""
+    feats, projs, gts, noises = [], [], [], []
+    g = torch.Generator().manual_seed(seed)
+    for s in range(4):
+        h, w = syn.stage_shape(h0, w0, s)
+        feats.append([syn.smooth_features(1, syn.STAGE_CHANNELS[s], h, w, seed * 100 + 10 * s + v) for v in range(nviews)])
+        projs.append(torch.from_numpy(syn.proj_matrices(jitter_index + 1, nviews, h0, w0, s,
+                                                         per_batch_jitter=0.02)[jitter_index:jitter_index + 1]))
+        gts.append(scene_gt_inverse_depth(seed, h, w))
+        noises.append(torch.randn((1, syn.STAGE_NDEPTHS[s], h, w), generator=g) * 0.5)
+    return {"features": feats, "projs": projs, "depth_values": torch.from_numpy(syn.depth_values(1)),
+            "gt": gts, "noise": noises}
+
+
+def fill_plan(plan, rank: int):
+    """Upload rank ``rank``'s batch of scenes (``make_scene(scene_seed(rank, i))``) and pre-compute the stand-in regnet
+    outputs for the hypotheses the cascade really visits (one untimed set-up pass)."""
+    gts = [torch.empty((plan.B,) + tuple(sh), device=plan.device) for sh in plan.shapes]
+    noises = [torch.empty_like(l) for l in plan.logits]
+    for i in range(plan.B):
+        sc = make_scene(scene_seed(rank, i), plan.N, plan.h0, plan.w0, jitter_index=i)
+        for s in range(plan.nstage):
+            for v in range(plan.N):
+                plan.features[s][v][i].copy_(sc["features"][s][v][0].permute(1, 2, 0))
+            plan.proj[s][i].copy_(sc["projs"][s][0])
+            gts[s][i].copy_(sc["gt"][s][0])
+            noises[s][i].copy_(sc["noise"][s][0])
+        plan.depth_values[i].copy_(sc["depth_values"][0])
+        del sc
 
     def regnet(s, _volume):
         plan.logits[s].copy_(tracking_logits(plan.hypo[s], gts[s], noises[s]))
@@ -189,37 +210,45 @@ def fill_plan(plan, seed: int):
     torch.cuda.synchronize()
 
 
-def cpu_workload(nviews, h0, w0, seed):
-    """One scene (B=1) of the same workload on the CPU for the oracle port."""
-    feats, projs, logits = [], [], []
-    g = torch.Generator().manual_seed(seed)
-    for s in range(4):
-        h, w = syn.stage_shape(h0, w0, s)
-        feats.append([syn.smooth_features(1, syn.STAGE_CHANNELS[s], h, w, seed * 100 + 10 * s + v) for v in range(nviews)])
-        projs.append(torch.from_numpy(syn.proj_matrices(1, nviews, h0, w0, s)))
-        gt = gt_inverse_depth(1, h, w, seed, "cpu")
-        noise = torch.randn((1, syn.STAGE_NDEPTHS[s], h, w), generator=g) * 0.5
-        logits.append(lambda hypo, gt=gt, noise=noise: tracking_logits(hypo, gt, noise))
-    return feats, projs, torch.from_numpy(syn.depth_values(1)), logits
-
-
-def run_cpu_port(args, steps, warmup):
-    """The reference algorithm on the host cores (oracle port, all threads).  One step = one scene."""
-    from oracle import mvster_oracle as O
+def run_reference_arm(args, steps, warmup, device="cpu"):
+    """The reference's own implementation of the path on ``device``: the UNMODIFIED reference (``oracle/_ref``) through
+    ``MVS4net.forward`` when it is present (kind "reference"), else the oracle's op-for-op torch port (kind "port").
+    One step = one scene of rank 0's batch (``make_scene(scene_seed(0, i))``, the scenes the GPU arm uploads)."""
+    from oracle import ref_arm
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    feats, projs, dv, logits = cpu_workload(args.views, args.height, args.width, 0)
+    if device == "cpu":
+        torch.set_num_threads(cores)
+    nscene = max(1, min(args.scenes, warmup + steps))
+    scenes = [make_scene(scene_seed(0, i), args.views, args.height, args.width, jitter_index=i) for i in range(nscene)]
+    runners = []
+    for sc in scenes:
+        mk = [lambda hypo, gt=sc["gt"][s].to(device), nz=sc["noise"][s].to(device): tracking_logits(hypo, gt, nz) for s in range(4)]
+        if ref_arm.available():
+            runners.append(ref_arm.ReferenceCascade(torch, sc["features"], sc["projs"], sc["depth_values"], mk,
+                                                    syn.STAGE_GROUPS, syn.STAGE_NDEPTHS, syn.STAGE_SPLIT_ITV, 2.0, device).run)
+        else:
+            from oracle import mvster_oracle as O
+            runners.append(lambda sc=sc, mk=mk: O.cascade_port(sc["features"], sc["projs"], sc["depth_values"], mk,
+                                                               syn.STAGE_GROUPS, syn.STAGE_NDEPTHS, syn.STAGE_SPLIT_ITV, 2.0))
+    kind = "reference" if ref_arm.available() else "port"
+    sync = (lambda: torch.cuda.synchronize()) if device != "cpu" else (lambda: None)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
+            sync()
             t0 = time.perf_counter()
-            O.cascade_port(feats, projs, dv, logits, syn.STAGE_GROUPS, syn.STAGE_NDEPTHS, syn.STAGE_SPLIT_ITV, 2.0)
+            runners[i % nscene]()
+            sync()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": steps / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d scene(s) of the same %dx%d N=%d 4-stage workload (B=1 per step), oracle torch-CPU port "
-                      "with %d threads, %d warm-up" % (steps, args.height, args.width, args.views, cores, warmup),
+    what = ("the unmodified reference (oracle/_ref: MVS4net.forward -> stage loop, schedule_inverse_range, stagenet / "
+            "homo_warping / attention / tail; FPN4 and reg2d replaced by the same stand-ins as in the GPU arm)"
+            if kind == "reference" else "oracle torch port of the reference op sequence (oracle/_ref absent)")
+    return {"value": steps / total, "unit": UNIT, "cores": cores if device == "cpu" else 0, "kind": kind,
+            "sample": "%d scene(s) (B=1 per step, %d warm-up) of rank 0's batch of the same %dx%d N=%d 4-stage workload: %s, "
+                      "%s" % (steps, warmup, args.height, args.width, args.views, what,
+                              ("%d host threads" % cores) if device == "cpu" else "eager PyTorch on the same GPU"),
             "ms_per_step": 1e3 * total / steps}
 
 
@@ -296,14 +325,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        # the reference's own CPU implementation of the path (oracle port): rank 0 only, other ranks exit quietly
+        # the reference's own CPU implementation of the path (oracle/_ref, else the oracle port): rank 0 only, the
+        # other ranks exit quietly.  Same config dictionary as the GPU arm (the workload is the same; what one step of
+        # this arm samples from it is said in cpu_baseline.sample).
         if rank != 0:
             return 0
-        res = run_cpu_port(args, max(1, args.steps), max(0, args.warmup))
+        res = run_reference_arm(args, max(1, args.steps), max(0, args.warmup))
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, 1), "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "config": workload_config(args, max(world, args.gpus)),
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -331,7 +363,7 @@ def main():
 
     fdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     plan = CascadePlan(args.scenes, args.views, args.height, args.width, device=dev, feature_dtype=fdt)
-    fill_plan(plan, 1234 + rank)
+    fill_plan(plan, rank)
     dom = plan.nstage - 1  # dominant kernel: stage-4 K1 forward
     sampler = ClockSampler(dev)
 
@@ -374,6 +406,19 @@ def main():
         torch.cuda.synchronize()
         plan.stage_events = None
     k1_ms = statistics.mean(a.elapsed_time(b) for a, b in pairs)
+    # every stage's K1 launch, bracketed the same way (eager passes after the timed region)
+    stage_ms = []
+    for st in range(plan.nstage):
+        if st == dom:
+            stage_ms.append(k1_ms)
+            continue
+        sp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 20))]
+        for p_ in sp:
+            plan.stage_events = p_
+            plan.run(time_stage=st)
+        torch.cuda.synchronize()
+        plan.stage_events = None
+        stage_ms.append(statistics.mean(a.elapsed_time(b) for a, b in sp))
 
     # ---- e2e leg: pinned host buffers in, depth + confidence out, every step ---------------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 10)
@@ -396,19 +441,30 @@ def main():
     e2e_ms = e_start.elapsed_time(e_end)
 
     # ---- max over ranks -------------------------------------------------------------------------------------------
-    t = torch.tensor([ms_total, e2e_ms, k1_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, e2e_ms, k1_ms] + stage_ms, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, k1_ms = (float(x) for x in t.tolist())
+    ms_total, e2e_ms, k1_ms = (float(x) for x in t.tolist()[:3])
+    stage_ms = [float(x) for x in t.tolist()[3:]]
 
     # ---- secondary: the whole MVS4net.forward around the hot path (SURVEY 8d row ii), rank 0 at N=1 only ---------------
     network = None
     if rank == 0 and world == 1 and not args.no_network and args.dtype == "fp32":
         network = run_network(args, dev)
 
-    cpu = None
+    cpu = gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu_port(args, args.cpu_scenes, 1)
+        from oracle import ref_arm
+        if ref_arm.available():
+            # SURVEY 8d row iii: the stock reference on this same GPU (eager ATen kernels), same scenes, B=1 per call
+            try:
+                gpu_ref = run_reference_arm(args, 8, 2, device=str(dev))
+                gpu_ref = {"value": gpu_ref["value"], "unit": UNIT, "ms_per_depth_map": gpu_ref["ms_per_step"],
+                           "kind": gpu_ref["kind"], "sample": gpu_ref["sample"]}
+            except Exception as exc:  # a baseline, never a reason to lose the bench line
+                print("[bench] gpu_reference failed: %s" % exc, file=sys.stderr)
+            torch.cuda.empty_cache()
+        cpu = run_reference_arm(args, args.cpu_scenes, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -424,25 +480,32 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "fp32" else "bf16 features, f32 accumulate", "data": "synthetic",
-            "config": dict(workload_config(args, world), host_affinity=(
-                "each rank bound to its GPU's local NUMA CPUs (%d cpus on rank 0)" % len(numa_cpus)) if numa_cpus
-                else "unbound (single rank, topology not exposed, or --no-numa-bind)"),
+            "config": workload_config(args, world),
+            "host_affinity": ("each rank bound to its GPU's local NUMA CPUs (%d cpus on rank 0)" % len(numa_cpus))
+                             if numa_cpus else "unbound (single rank, topology not exposed, or --no-numa-bind)",
             "clocks": sampler.summary(),
             "e2e": {"value": args.scenes * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": plan.h2d_bytes(), "d2h_bytes_per_step": plan.d2h_bytes(),
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "CascadePlan.run_from_host (pinned host features/cameras in, depth+confidence out)"},
             "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
-            "roofline": {"kernel": "epi_fwd_kernel<C=8,CPG=2,D=4> (stage-4 K1 forward)", "bound": "hbm",
+            "roofline": {"kernel": "epi_fwd_box_kernel<C=8,CPG=2,D=4> (stage-4 K1 forward)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": k1_ms, "fp32_fma_bound_ms": fma_ms,
-                         "hbm_bound_ms": alg_bytes / (peak * 1e9) * 1e3},
+                         "hbm_bound_ms": alg_bytes / (peak * 1e9) * 1e3,
+                         "per_stage": [{"stage": st + 1, "kernel_ms": stage_ms[st],
+                                        "algorithmic_bytes_per_launch": plan.k1_bytes(st),
+                                        "achieved": plan.k1_bytes(st) / (stage_ms[st] * 1e-3) / 1e9,
+                                        "frac": plan.k1_bytes(st) / (stage_ms[st] * 1e-3) / 1e9 / peak}
+                                       for st in range(plan.nstage)]},
         }
         if network is not None:
             line["whole_network"] = network
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -187,3 +187,18 @@ def fill_state_dict(state_dict, seed: int = 0):
             arr = rng.normal(0.0, 0.05, size=shape)
         out[key] = torch.from_numpy(np.asarray(arr)).to(val.dtype)
     return out
+
+
+def filter_fixture_512(views: int = 3, h: int = 512, w: int = 640):
+    """Deterministic inputs of the full-size filter golden (``tests/golden/filter512.npz`` holds only the reference's
+    OUTPUTS for these inputs plus a checksum of them): ``views`` cameras of the 0.05-rad rig looking at the analytic
+    surface, depth noise 0.3 mm, a hole in every depth map and one inconsistent patch."""
+    k = intrinsics(h, w, 3)
+    es = [extrinsics(i, 0.05, tilt_rad=0.01) for i in range(views)]
+    depths = render_surface_depths(k, es, h, w, noise_mm=0.3, seed=7)
+    for v in range(views):
+        depths[v, 40 + 30 * v:60 + 30 * v, 100 + 50 * v:140 + 50 * v] = 0.0
+    depths[1, 300:340, 200:280] += 20.0
+    conf = np.random.RandomState(5).uniform(0, 1, size=(views, h, w)).astype(np.float32)
+    pairs = np.concatenate([np.arange(views)[:, None], pair_list(views, views - 1)], 1).astype(np.int32)
+    return depths, conf, np.stack([k] * views), np.stack(es), pairs

@@ -28,7 +28,7 @@ int main() {
     cudaMalloc(&d_offs, 32 * 4); cudaMalloc(&d_out, 32 * 4);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     auto sw = [](int texel, int chunk) { int g = 2 * texel + chunk; return g ^ ((g >> 3) & 1); };  // 32B swizzle, 16B units
-    struct Pat { const char* name; int o[32]; } pats[16];
+    struct Pat { const char* name; int o[32]; } pats[32];
     int np = 0;
     auto add = [&](const char* n, auto f) { pats[np].name = n; for (int l = 0; l < 32; ++l) pats[np].o[l] = f(l); ++np; };
     add("P0 consecutive texels, swizzled chunk0 (expect 4)", [&](int l) { return sw(l, 0); });
@@ -44,6 +44,13 @@ int main() {
     add("P10 lanes 0-7: texel l chunk0 but lane 7 in next row (+48 texels)", [&](int l) { int q = l / 8, i = l % 8; return sw(q * 8 + i + (i == 7 ? 48 : 0), 0); });
     add("P11 lanes 0-7: two lanes share a texel, one skipped twice", [&](int l) { int q = l / 8, i = l % 8; int t[8] = {0, 1, 1, 2, 3, 5, 6, 8}; return sw(q * 16 + t[i], 0); });
     add("P12 even lanes unit l/2, odd lanes unit 8+l/2 within 16 lanes: 2 addr per bank group per quarter?", [&](int l) { return (l & 1) ? 8 + (l % 16) / 2 : (l % 16) / 2; });
+    add("P13 one duplicate per quarter {0,1,2,3,3,4,5,6}, swizzled chunk0", [&](int l) { int q = l / 8, i = l % 8; int t[8] = {0, 1, 2, 3, 3, 4, 5, 6}; return sw(q * 8 + t[i], 0); });
+    add("P14 duplicate at start {0,0,1,2,3,4,5,6}", [&](int l) { int q = l / 8, i = l % 8; int t[8] = {0, 0, 1, 2, 3, 4, 5, 6}; return sw(q * 8 + t[i], 0); });
+    add("P15 two duplicates {0,0,1,2,3,3,4,5}", [&](int l) { int q = l / 8, i = l % 8; int t[8] = {0, 0, 1, 2, 3, 3, 4, 5}; return sw(q * 8 + t[i], 0); });
+    add("P16 warp-continuous texels with scale 0.9: t = floor(0.9*l)", [&](int l) { return sw((int)(0.9f * l), 0); });
+    add("P17 warp-continuous scale 0.9 offset 3: t = 3 + floor(0.9*l+0.5)", [&](int l) { return sw(3 + (int)(0.9f * l + 0.5f), 0); });
+    add("P18 quarter duplicates unswizzled 16B units {0,1,2,3,3,4,5,6}", [&](int l) { int q = l / 8, i = l % 8; int t[8] = {0, 1, 2, 3, 3, 4, 5, 6}; return q * 8 + t[i]; });
+    add("P19 pairs of lanes share a unit: {0,0,1,1,2,2,3,3}", [&](int l) { return l / 2; });
     for (int p = 0; p < np; ++p) {
         cudaMemcpy(d_offs, pats[p].o, 128, cudaMemcpyHostToDevice);
         probe<<<1, 32, 65536>>>(d_offs, d_out, 1000);

@@ -119,3 +119,29 @@ def test_remap_emulation_matches_cv2():
     ref = cv2.remap(img, mx, my, interpolation=cv2.INTER_LINEAR)
     got = O.remap_linear_np(img, mx, my)
     assert np.abs(ref - got).max() < 2e-4
+
+
+def test_filter_512x640_oracle_matches_the_lifted_reference():
+    """Full-size pin of the filter oracle: three 512x640 views, all pairs (tests/golden/make_golden_filter512.py)."""
+    import hashlib, os
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import synthetic as syn
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filter512.npz"))
+    depths, conf, ks, es, pairs = syn.filter_fixture_512()
+    sha = hashlib.sha256()
+    for a in (depths, conf, ks, es, pairs):
+        sha.update(np.ascontiguousarray(a).tobytes())
+    assert sha.hexdigest() == str(g["inputs_sha256"])
+    w = depths.shape[2]
+    want = np.unpackbits(g["pair_mask_bits"], axis=-1)[..., :w].astype(bool)
+    total = same = 0
+    for i, row in enumerate(pairs[:2]):            # two reference views = four pairs keep the CPU suite short
+        r = int(row[0])
+        for j, s in enumerate(row[1:]):
+            s = int(s)
+            m, d, _, _ = O.check_geometric_consistency_np(depths[r], ks[r], es[r], depths[s], ks[s], es[s],
+                                                          float(g["condmask_pixel"]), float(g["condmask_depth"]))
+            total += m.size
+            same += int((m == want[i, j]).sum())
+            both = (m & want[i, j])[::4, ::4]
+            assert np.abs(d[::4, ::4][both] - g["pair_depth_reprojected_s4"][i, j][both]).max() < 2e-3
+    assert same / total >= 0.9999, same / total
