@@ -26,21 +26,9 @@ struct DeviceGuard {
 };
 
 // Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute is per (function, device): a process
-// that drives several GPUs (nn.DataParallel, reference test_mvs4.py:393) must set it once on each of them.
-template <typename Kernel>
-static inline int ensure_dynamic_smem(Kernel kernel, int bytes, bool (&done)[64], const char* what) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (!done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return check_cuda(e, what);
-        done[dev] = true;
-    }
-    return MVSTER_OK;
-}
-
-// Same for kernels whose dynamic shared-memory size depends on run-time arguments: remembers the largest size set
-// per device and raises the limit again when a later call needs more.  Safe to call from concurrent host threads.
+// that drives several GPUs (nn.DataParallel, reference test_mvs4.py:393) must set it once on each of them.  The
+// largest size set per device is remembered and the limit is raised again when a later call needs more (kernels whose
+// shared-memory size depends on run-time arguments, e.g. the Sinkhorn history).  Safe to call from concurrent host threads.
 template <typename Kernel>
 static inline int ensure_dynamic_smem_bytes(Kernel kernel, int bytes, int (&largest)[64], const char* what) {
     int dev = 0;

@@ -595,9 +595,9 @@ static int launch_bwd_tma(const EpiBwdTmaParams& pp, cudaStream_t stream) {
     constexpr int NT = 128, TB = C * 4, TILE_H = 4 / (C / 8);
     constexpr int SMEM = 2 * TmaGeom<C>::BW * (4 + TmaGeom<C>::BH_EXTRA) * TB + 1024 + TmaGeom<C>::CTL_BYTES +
                          MVSTER_MAX_SRC_VIEWS * 48;
-    static bool attr_done[64] = {};
+    static int attr_done[64] = {};  // largest size set per device
     if (SMEM > 48 * 1024) {
-        const int st = ensure_dynamic_smem(epi_bwd_tma_kernel<C, CPG, D>, SMEM, attr_done, "epi_bwd(tma): cudaFuncSetAttribute");
+        const int st = ensure_dynamic_smem_bytes(epi_bwd_tma_kernel<C, CPG, D>, SMEM, attr_done, "epi_bwd(tma): cudaFuncSetAttribute");
         if (st != MVSTER_OK) return st;
     }
     const EpiBwdParams& p = pp.q;

@@ -341,8 +341,8 @@ static bool make_line_maps(EpiFwdParams& p, int Nsrc, int B, int Hs, int Ws) {
 template <int CPG, int D>
 static int launch_line(const EpiFwdParams& p, cudaStream_t stream) {
     using Gm = LineGeom;
-    static bool attr_done[64] = {};
-    const int st = ensure_dynamic_smem(epi_fwd_line_kernel<CPG, D>, Gm::SMEM, attr_done, "epi_fwd(line): cudaFuncSetAttribute");
+    static int attr_done[64] = {};  // largest size set per device
+    const int st = ensure_dynamic_smem_bytes(epi_fwd_line_kernel<CPG, D>, Gm::SMEM, attr_done, "epi_fwd(line): cudaFuncSetAttribute");
     if (st != MVSTER_OK) return st;
     dim3 grid((p.W + Gm::TILE_W - 1) / Gm::TILE_W, (p.H + Gm::TILE_H - 1) / Gm::TILE_H, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_fwd: grid too large");

@@ -200,8 +200,8 @@ static int launch_topdown(const float* prev, const float* lat, const float* intr
     const int Hl = H / 2, Wl = W / 2;
     p.sy = H > 1 ? (float)(Hl - 1) / (float)(H - 1) : 0.f;  // ATen area_pixel_compute_scale, align_corners=True
     p.sx = W > 1 ? (float)(Wl - 1) / (float)(W - 1) : 0.f;
-    static bool attr_done[64] = {};
-    const int st = ensure_dynamic_smem(fpn_topdown_kernel<CL, CO>, kTdSmem, attr_done, "fpn_topdown: cudaFuncSetAttribute");
+    static int attr_done[64] = {};  // largest size set per device
+    const int st = ensure_dynamic_smem_bytes(fpn_topdown_kernel<CL, CO>, kTdSmem, attr_done, "fpn_topdown: cudaFuncSetAttribute");
     if (st != MVSTER_OK) return st;
     dim3 grid((W + kTdTW - 1) / kTdTW, (H + kTdTH - 1) / kTdTH, B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "fpn_topdown: grid too large");

@@ -286,9 +286,9 @@ __global__ void __launch_bounds__(256) sinkhorn_bwd_kernel(const float* grad_px,
 
 template <int D, bool CONT, int NT>
 static int launch_sinkhorn(const SinkhornParams& p, int smem, cudaStream_t s) {
-    static bool attr_done[64] = {};
+    static int attr_done[64] = {};  // largest size set per device
     if (smem > 48 * 1024) {
-        const int st = ensure_dynamic_smem(sinkhorn_kernel<D, CONT, NT>, smem, attr_done, "sinkhorn: cudaFuncSetAttribute");
+        const int st = ensure_dynamic_smem_bytes(sinkhorn_kernel<D, CONT, NT>, smem, attr_done, "sinkhorn: cudaFuncSetAttribute");
         if (st != MVSTER_OK) return st;
     }
     sinkhorn_kernel<D, CONT, NT><<<(unsigned)((p.total + NT - 1) / NT), NT, smem, s>>>(p);

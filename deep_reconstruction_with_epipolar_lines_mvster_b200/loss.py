@@ -24,7 +24,11 @@ class SinkhornLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous, inverse_depth, want_tmap=False):
-        need = attn_weight.requires_grad
+        # the in-kernel reverse sweep (shared-memory history, a [B,D,H,W] gradient buffer) only when autograd will
+        # actually ask for it: needs_input_grad is all-False under torch.no_grad() (validation passes on outputs that
+        # still carry requires_grad=True), unlike attn_weight.requires_grad
+        need = bool(ctx.needs_input_grad[2])
+        ctx.has_grad = need
         stats, grad_px, tmap = ops.sinkhorn_fwd(gt_depth, hypo_depth, attn_weight, mask, iters, eps, continuous,
                                                 inverse_depth, want_grad=need, want_tmap=want_tmap)
         if need:
@@ -36,6 +40,8 @@ class SinkhornLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_stats, _grad_tmap):
+        if not ctx.has_grad:
+            return None, None, None, None, None, None, None, None, None
         grad_px, stats = ctx.saved_tensors
         grad_attn = ops.sinkhorn_bwd(grad_px, stats, grad_stats.contiguous()[0:1])
         return None, None, grad_attn, None, None, None, None, None, None

@@ -47,7 +47,42 @@ class Conv2d(nn.Module):
         return F.relu(x, inplace=True) if self.relu else x
 
 
-class FPN4(nn.Module):
+class _FoldedWeights:
+    """Mixin of the modules that cache BatchNorm-folded eval-mode weights (host copies, device copies, kernel-parameter
+    slices).  The caches are keyed on the parameters' ``_version`` + ``data_ptr()``, which an in-place update through
+    ``.data`` (EMA swaps: ``p.data.copy_(ema)``) does NOT change: call ``invalidate_folded()`` after such an update.
+    It is called automatically by ``train()``, ``load_state_dict()`` and ``_apply()`` (``.to()``, ``.half()``...).
+    A ``GraphedMVS4net`` capture bakes the folded weights in as by-value kernel parameters: re-capture after any
+    weight change."""
+
+    def invalidate_folded(self):
+        for m in self.modules():
+            if isinstance(m, _FoldedWeights):
+                m._drop_folded()
+
+    def _drop_folded(self):
+        if hasattr(self, "_fold_cache"):
+            self._fold_cache = {}
+        if hasattr(self, "_folded") and not callable(getattr(self, "_folded")):
+            self._folded = None
+
+    def train(self, mode: bool = True):
+        self._drop_folded()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_folded()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._drop_folded()
+        return out
+
+
+
+class FPN4(_FoldedWeights, nn.Module):
     """Four-level feature pyramid, 8/4/2/1 x ``base_channels`` output channels at 1/8 .. 1/1 resolution
     (reference mvs4net_utils.py:426-509, ``gn=False, dcn=False``)."""
 
@@ -207,7 +242,7 @@ def _up3d(cin, cout):
         nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
 
 
-class reg2d(nn.Module):
+class reg2d(_FoldedWeights, nn.Module):
     """Cost regulariser (reference mvs4net_utils.py:884-926): a 3-level U-Net over (H, W) with (1,3,3) strided and
     (3,3,3) plain convolutions, ``[B, G, D, H, W] -> [B, D, H, W]`` logits.
 
@@ -353,7 +388,7 @@ class reg2d(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------------
 # the network
 # ----------------------------------------------------------------------------------------------------------------------
-class MVS4net(nn.Module):
+class MVS4net(_FoldedWeights, nn.Module):
     """Reference ``MVS4net`` (models/MVS4Net.py:16) on the B200 hot path: same constructor arguments, same
     ``forward(imgs, proj_matrices, depth_values, filename=None)`` and the same nested output dictionary."""
 

@@ -102,26 +102,37 @@ def compose_homography_pair(src_proj: torch.Tensor, ref_proj: torch.Tensor) -> t
     return rt
 
 
+def _check_k1_inputs(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch.Tensor, hypo: torch.Tensor):
+    """Shape / dtype / device / contiguity contract shared by every K1 entry point (the kernels index raw pointers:
+    a smaller or foreign source map would be read out of bounds, not rejected).  Returns ``(hypo fp32 contiguous, d)``."""
+    _require_cuda(ref_nhwc, "ref")
+    if ref_nhwc.dim() != 4 or not ref_nhwc.is_contiguous():
+        raise RuntimeError("ref features must be contiguous NHWC [B,H,W,C]")
+    b, h, w, c = ref_nhwc.shape
+    nsrc = len(srcs_nhwc)
+    if nsrc == 0:
+        raise RuntimeError("at least one source view is required")
+    for s in srcs_nhwc:
+        if s.dim() != 4 or s.shape != srcs_nhwc[0].shape or s.shape[0] != b or s.shape[3] != c or s.dtype != ref_nhwc.dtype \
+                or not s.is_contiguous() or s.device != ref_nhwc.device:
+            raise RuntimeError("source features must share shape [B,Hs,Ws,C], dtype, device and be contiguous")
+    hypo = _f32c(hypo, "depth_hypo")
+    if hypo.dim() != 4 or hypo.device != ref_nhwc.device or tuple(hypo.shape) != (b, hypo.shape[1], h, w):
+        raise RuntimeError("depth_hypo must be [B,D,H,W] = [%d,D,%d,%d] on %s, got %s" % (b, h, w, ref_nhwc.device,
+                                                                                         tuple(hypo.shape)))
+    if tuple(rt.shape) != (b, nsrc, 12) or rt.dtype != torch.float32 or not rt.is_contiguous() or rt.device != ref_nhwc.device:
+        raise RuntimeError("rt must be contiguous fp32 [B,Nsrc,12] on the features' device")
+    return hypo, hypo.shape[1]
+
+
 def epi_fwd(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch.Tensor, hypo: torch.Tensor,
             groups: int, attn_temp: float, want_wsum: bool = False, want_weights: bool = False
             ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
     """Fused K1 forward on NHWC features.  Returns ``(volume [B,G,D,H,W], wsum or None, weights or None)``."""
-    _require_cuda(ref_nhwc, "ref")
+    hypo, d = _check_k1_inputs(ref_nhwc, srcs_nhwc, rt, hypo)
     b, h, w, c = ref_nhwc.shape
     nsrc = len(srcs_nhwc)
     hs, ws = srcs_nhwc[0].shape[1:3]
-    for s in srcs_nhwc:
-        if s.shape != srcs_nhwc[0].shape or s.shape[0] != b or s.shape[3] != c or s.dtype != ref_nhwc.dtype \
-                or not s.is_contiguous() or s.device != ref_nhwc.device:
-            raise RuntimeError("source features must share shape [B,Hs,Ws,C], dtype, device and be contiguous")
-    if not ref_nhwc.is_contiguous():
-        raise RuntimeError("ref features must be contiguous NHWC")
-    hypo = _f32c(hypo, "depth_hypo")
-    d = hypo.shape[1]
-    if tuple(hypo.shape) != (b, d, h, w):
-        raise RuntimeError("depth_hypo must be [B,D,H,W] = [%d,D,%d,%d], got %s" % (b, h, w, tuple(hypo.shape)))
-    if tuple(rt.shape) != (b, nsrc, 12) or rt.dtype != torch.float32 or not rt.is_contiguous():
-        raise RuntimeError("rt must be contiguous fp32 [B,Nsrc,12]")
     dev = ref_nhwc.device
     out = torch.empty((b, groups, d, h, w), device=dev, dtype=torch.float32)
     wsum = torch.empty((b, d, h, w), device=dev, dtype=torch.float32) if want_wsum else None
@@ -135,14 +146,10 @@ def epi_fwd(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch
 def epi_fwd_mode(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch.Tensor, hypo: torch.Tensor,
                  groups: int, attn_temp: float, group_cor: bool, attn_fuse_d: bool) -> torch.Tensor:
     """Forward of the reference's non-default options (variance cost / per-pixel weight); inference only."""
-    _require_cuda(ref_nhwc, "ref")
+    hypo, d = _check_k1_inputs(ref_nhwc, srcs_nhwc, rt, hypo)
     b, h, w, c = ref_nhwc.shape
     nsrc = len(srcs_nhwc)
     hs, ws = srcs_nhwc[0].shape[1:3]
-    hypo = _f32c(hypo, "depth_hypo")
-    d = hypo.shape[1]
-    if tuple(hypo.shape) != (b, d, h, w):
-        raise RuntimeError("depth_hypo must be [B,D,H,W]")
     g = groups if group_cor else c
     out = torch.empty((b, g, d, h, w), device=ref_nhwc.device, dtype=torch.float32)
     _lib.check(_lib.load().mvster_epi_fwd_mode(
@@ -154,11 +161,13 @@ def epi_fwd_mode(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: 
 def epi_bwd(ref_nhwc, srcs_nhwc, rt, hypo, out, wsum, gout, groups: int, attn_temp: float
             ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """K1 backward.  Returns ``(grad_ref [B,H,W,C] fp32, [grad_src_v [B,Hs,Ws,C] fp32])``."""
+    hypo, d = _check_k1_inputs(ref_nhwc, srcs_nhwc, rt, hypo)
     b, h, w, c = ref_nhwc.shape
     nsrc = len(srcs_nhwc)
     hs, ws = srcs_nhwc[0].shape[1:3]
-    d = hypo.shape[1]
     gout = _f32c(gout, "grad_output")
+    if tuple(gout.shape) != (b, groups, d, h, w) or tuple(out.shape) != (b, groups, d, h, w) or tuple(wsum.shape) != (b, d, h, w):
+        raise RuntimeError("grad_output / out must be [B,G,D,H,W] and wsum [B,D,H,W] of the forward call")
     dev = ref_nhwc.device
     grad_ref = torch.empty((b, h, w, c), device=dev, dtype=torch.float32)
     grad_all = torch.zeros((nsrc, b, hs, ws, c), device=dev, dtype=torch.float32)  # one memset for all views
@@ -171,8 +180,15 @@ def epi_bwd(ref_nhwc, srcs_nhwc, rt, hypo, out, wsum, gout, groups: int, attn_te
 
 
 def homo_warp(src_nhwc: torch.Tensor, rt: torch.Tensor, hypo: torch.Tensor) -> torch.Tensor:
+    _require_cuda(src_nhwc, "src")
+    if src_nhwc.dim() != 4 or not src_nhwc.is_contiguous():
+        raise RuntimeError("src features must be contiguous NHWC [B,Hs,Ws,C]")
     b, hs, ws, c = src_nhwc.shape
     hypo = _f32c(hypo, "depth_values")
+    if hypo.dim() != 4 or hypo.shape[0] != b or hypo.device != src_nhwc.device:
+        raise RuntimeError("depth_values must be [B,D,H,W] with the features' batch size and device")
+    if tuple(rt.shape) != (b, 12) or rt.dtype != torch.float32 or not rt.is_contiguous() or rt.device != src_nhwc.device:
+        raise RuntimeError("rt must be contiguous fp32 [B,12] on the features' device")
     _, d, h, w = hypo.shape
     out = torch.empty((b, c, d, h, w), device=src_nhwc.device, dtype=torch.float32)
     _lib.check(_lib.load().mvster_homo_warp(_ptr(src_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), b, c, d, h, w, hs, ws,

@@ -64,6 +64,7 @@ class CascadePlan:
         self._src_ptrs = [ops._ptr_array(fs[1:]) for fs in self.features]
         self.regnet: Optional[Callable[[int, torch.Tensor], torch.Tensor]] = None
         self.stage_events = None  # optional [(start, end)] CUDA events around one stage's K1 launch
+        self.graph = None         # set by capture()
 
     # ---- sizes for the roofline (algorithmic bytes of K1 forward) ---------------------------------
     def k1_bytes(self, stage: int) -> int:
@@ -130,6 +131,11 @@ class CascadePlan:
         return self
 
     def replay(self):
+        if self.graph is None:
+            raise RuntimeError("CascadePlan.replay(): call capture() first")
+        if self.regnet is not None:
+            raise RuntimeError("CascadePlan.replay(): the captured graph uses the resident stand-in logits; a regnet "
+                               "callback assigned after capture() would be ignored - use run() instead")
         self.graph.replay()
         return self.depth[-1], self.conf[-1]
 

@@ -457,3 +457,45 @@ def test_fuse_scene_matches_reference_point_cloud(golden):
         assert verts.shape == g["vertices"].shape
         assert np.abs(verts.cpu().numpy() - g["vertices"]).max() < 2e-3       # averaged depth is fp32: ~1e-4 mm
         assert np.array_equal(cols.cpu().numpy(), g["colors"])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# argument contracts added after the round-1 review
+# --------------------------------------------------------------------------------------------------------------
+def test_k1_entry_points_reject_mismatched_sources():
+    """Every K1 entry point validates the source maps (a smaller or foreign-device map would be read out of bounds)."""
+    b, h, w, c, d = 1, 16, 24, 8, 4
+    ref = torch.zeros((b, h, w, c), device=DEV)
+    good = torch.zeros((b, h, w, c), device=DEV)
+    small = torch.zeros((b, h - 4, w, c), device=DEV)
+    rt = torch.zeros((b, 2, 12), device=DEV)
+    hypo = torch.ones((b, d, h, w), device=DEV)
+    for bad in ([good, small], [good, good.double()], [good, good[:, :, ::2]]):
+        with pytest.raises(RuntimeError, match="source features"):
+            ops.epi_fwd_mode(ref, bad, rt, hypo, 4, 2.0, False, True)
+        with pytest.raises(RuntimeError, match="source features"):
+            ops.epi_fwd(ref, bad, rt, hypo, 4, 2.0)
+    with pytest.raises(RuntimeError, match="rt must be"):
+        ops.epi_fwd_mode(ref, [good, good], rt[:, :1].contiguous(), hypo, 4, 2.0, False, True)
+    with pytest.raises(RuntimeError, match="depth_values|rt must be"):
+        ops.homo_warp(good, torch.zeros((b + 1, 12), device=DEV), hypo)
+
+
+def test_cascade_plan_replay_guards():
+    from deep_reconstruction_with_epipolar_lines_mvster_b200.pipeline import CascadePlan
+    plan = CascadePlan(1, 3, 64, 96, device=DEV)
+    with pytest.raises(RuntimeError, match="capture"):
+        plan.replay()
+    for s in range(4):
+        for f in plan.features[s]:
+            f.normal_()
+        plan.proj[s].copy_(torch.from_numpy(syn.proj_matrices(1, 3, 64, 96, s)))
+    plan.depth_values.copy_(torch.from_numpy(syn.depth_values(1)))
+    plan.capture()
+    d0, _ = plan.replay()
+    d0 = d0.clone()
+    d1, _ = plan.run()
+    assert torch.equal(d0, d1)
+    plan.regnet = lambda s, vol: plan.logits[s]
+    with pytest.raises(RuntimeError, match="regnet"):
+        plan.replay()

@@ -132,3 +132,35 @@ def test_empty_mask_is_nan_and_bad_arguments_raise():
         ops.sinkhorn_fwd(gt, hypo, attn, gt > 0, 100000, 1.0, False)                                    # history too long
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.sinkhorn_fwd(gt.cpu(), hypo.cpu(), attn.cpu(), (gt > 0).cpu(), 3, 1.0, False)
+
+
+def test_history_limit_grows_within_one_process():
+    """the kernel's dynamic shared-memory limit follows the largest request on the device - a call
+    with ot_iter=10 (80 KB of history at D=8) followed by one with ot_iter=20 (160 KB) must not fail."""
+    gen = torch.Generator().manual_seed(3)
+    b, d, h, w = 1, 8, 6, 40
+    hypo = torch.sort(torch.rand(b, d, h, w, generator=gen) * 300 + 500, 1, descending=True)[0].to(DEV)
+    gt = (torch.rand(b, h, w, generator=gen) * 300 + 500).to(DEV)
+    mask = torch.ones(b, h, w, dtype=torch.bool, device=DEV)
+    for iters in (10, 20, 10):
+        a = torch.softmax(torch.randn(b, d, h, w, generator=gen), 1).to(DEV).requires_grad_(True)
+        stats, _ = L.SinkhornLoss.apply(gt, hypo, a, mask, iters, 1.0, False, False)
+        stats[0].backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(stats[0]) and torch.isfinite(a.grad).all()
+
+
+def test_no_backward_sweep_under_no_grad():
+    """A validation pass under torch.no_grad() on outputs that still require grad must not run the in-kernel backward
+    (no history, no gradient buffer) and must give the same loss."""
+    gen = torch.Generator().manual_seed(5)
+    b, d, h, w = 2, 4, 8, 24
+    hypo = torch.sort(torch.rand(b, d, h, w, generator=gen) * 300 + 500, 1, descending=True)[0].to(DEV)
+    gt = (torch.rand(b, h, w, generator=gen) * 300 + 500).to(DEV)
+    mask = (torch.rand(b, h, w, generator=gen) > 0.3).to(DEV)
+    a = torch.softmax(torch.randn(b, d, h, w, generator=gen), 1).to(DEV).requires_grad_(True)
+    stats, _ = L.SinkhornLoss.apply(gt, hypo, a, mask, 3, 1.0, False, False)
+    with torch.no_grad():
+        stats_ng, _ = L.SinkhornLoss.apply(gt, hypo, a, mask, 3, 1.0, False, False)
+    assert not stats_ng.requires_grad
+    assert torch.equal(stats.detach(), stats_ng)
