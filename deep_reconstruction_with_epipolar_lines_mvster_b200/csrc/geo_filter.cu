@@ -26,6 +26,7 @@ struct PairCam {
     double F[9], f[3];
     double G[9], g[3];
     double Bz[3], tbz;
+    float Gf[9], gf[3], Bzf[3], tbzf;  // float32 copies of the back-projection for the fast path (see check_pair)
     int src;  // source view index (into the depth stack), < 0 = skip
     int pad;
 };
@@ -42,10 +43,9 @@ __device__ __forceinline__ void mat3_vec(const double* m, double x, double y, do
 // INTER_BITS=5 (cvRound = round-half-even of x*32), tap = floor, weights = (frac/32) products in float32.
 __device__ __forceinline__ float remap_linear(const float* __restrict__ img, int H, int W, float mx, float my) {
     if (!(isfinite(mx) && isfinite(my))) return 0.0f;
-    const double xs = fmin(fmax((double)mx * 32.0, -1e8), 1e8);
-    const double ys = fmin(fmax((double)my * 32.0, -1e8), 1e8);
-    const int ix = __double2int_rn(xs);
-    const int iy = __double2int_rn(ys);
+    // x * 32 is exact in float32 (a power of two), so rounding the float product equals rounding the double one
+    const int ix = __float2int_rn(fminf(fmaxf(mx * 32.0f, -1e8f), 1e8f));
+    const int iy = __float2int_rn(fminf(fmaxf(my * 32.0f, -1e8f), 1e8f));
     const int x0 = ix >> 5, y0 = iy >> 5;
     const float fx = (float)(ix & 31) * (1.0f / 32.0f);
     const float fy = (float)(iy & 31) * (1.0f / 32.0f);
@@ -70,6 +70,28 @@ struct PairResult {
     float x_src, y_src;
 };
 
+// 1 / x in float64 without the IEEE-division slow path: MUFU.RCP64H seed + two Newton steps (<= 2 ulp).  The
+// quotients only feed values that are rounded to float32 (the remap coordinates) or compared with a threshold, so
+// a last-bit difference from a correctly rounded division moves a result with probability ~1e-9.
+__device__ __forceinline__ double fast_rcp64(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// The reference does everything in float64.  Here only what needs it does:
+//   * reference pixel -> source pixel stays float64: the remap coordinate is rounded to 1/32 px, and a float32 chain
+//     (error ~2e-4 px) would pick the neighbouring sub-pixel bin for ~2.6 % of the pixels;
+//   * the back-projection runs in float32 (errors ~1e-4 px / ~1.5e-7 relative depth against thresholds of 1 px / 1 %),
+//     and only a pixel whose squared distance is within 0.8 % of the threshold or whose relative depth difference is
+//     within 0.03 % of its threshold (fp32 worst case: 7e-4 / 3e-5 of the thresholds at 640-px coordinates) is redone in float64 (EXACT = the reference arithmetic) - a fraction of a percent
+//     of the pixels, so the masks are those of the float64 chain; depth_reprojected differs from the float64 value
+//     by a few float32 ulps (tolerance of the parity tests: 2e-3).
+// B200 issues DFMA at half rate and every float<->double conversion goes through the quarter-rate XU pipe: the
+// all-float64 version was issue-bound at 82 % (profiles/r02_filter_ncu.md).
 __device__ __forceinline__ PairResult check_pair(const PairCam& c, const float* __restrict__ depth_src, int H, int W,
                                                  int x, int y, float d_ref, double pix_thr2, float rel_thr) {
     PairResult r;
@@ -78,12 +100,29 @@ __device__ __forceinline__ PairResult check_pair(const PairCam& c, const float* 
     double qx, qy, qz;
     mat3_vec(c.F, (double)x * dr, (double)y * dr, dr, qx, qy, qz);
     qx += c.f[0]; qy += c.f[1]; qz += c.f[2];
-    const double iq = 1.0 / qz;
+    const double iq = fast_rcp64(qz);
     const double u = qx * iq, v = qy * iq;
     r.x_src = (float)u;  // :630-631
     r.y_src = (float)v;
     // step 2: sample the source depth and project back (:632-647)
     const float ds = remap_linear(depth_src, H, W, r.x_src, r.y_src);
+    const float fxr = (float)x, fyr = (float)y;
+    {   // float32 back-projection
+        const float ux = r.x_src * ds, vx = r.y_src * ds;
+        const float px = fmaf(c.Gf[0], ux, fmaf(c.Gf[1], vx, fmaf(c.Gf[2], ds, c.gf[0])));
+        const float py = fmaf(c.Gf[3], ux, fmaf(c.Gf[4], vx, fmaf(c.Gf[5], ds, c.gf[1])));
+        const float pz = fmaf(c.Gf[6], ux, fmaf(c.Gf[7], vx, fmaf(c.Gf[8], ds, c.gf[2])));
+        r.depth_reprojected = fmaf(c.Bzf[0], ux, fmaf(c.Bzf[1], vx, fmaf(c.Bzf[2], ds, c.tbzf)));
+        const float ip = fast_rcp(pz);
+        const float dx = px * ip - fxr, dy = py * ip - fyr;
+        const float dist2 = fmaf(dx, dx, dy * dy);
+        const float rel = fabsf(r.depth_reprojected - d_ref) / d_ref;
+        const float thr2 = (float)pix_thr2;
+        r.mask = (dist2 < thr2) && (rel < rel_thr);
+        const bool near = (fabsf(dist2 - thr2) < 0.008f * thr2) || (fabsf(rel - rel_thr) < 3e-4f * rel_thr);
+        if (!near) return r;
+    }
+    // EXACT: the reference's float64 chain for the few pixels next to a threshold
     const double dsd = (double)ds;
     const double ux = u * dsd, vx = v * dsd;
     double px, py, pz;
@@ -242,6 +281,9 @@ static void make_pair_cam(const double* Kr, const double* Er, const double* Ks, 
         c->Bz[i] = Bk[6 + i];
     }
     c->tbz = back[11];
+    for (int i = 0; i < 9; ++i) c->Gf[i] = (float)c->G[i];
+    for (int i = 0; i < 3; ++i) { c->gf[i] = (float)c->g[i]; c->Bzf[i] = (float)c->Bz[i]; }
+    c->tbzf = (float)c->tbz;
     c->src = src;
     c->pad = 0;
 }
