@@ -46,6 +46,9 @@
 #ifndef MVSTER_BOX_WIDE_MINB
 #define MVSTER_BOX_WIDE_MINB 3
 #endif
+#ifndef MVSTER_BOX_SPLIT_A
+#define MVSTER_BOX_SPLIT_A 1   // plan and request view 0 before the other views' boxes are reduced (A/B: stage 4 0.656 -> 0.628 ms, stage 3 0.332 -> 0.323 ms)
+#endif
 #ifndef MVSTER_BOX_KO
 #define MVSTER_BOX_KO 0    // development only, WRONG RESULTS: knock-out bits (1: no gather LDS, 2: no TMA - the boxes hold garbage, 4: no blend math)
 #endif
@@ -56,7 +59,11 @@ namespace mvster {
 template <int C, int D, int ES, int BWT = MVSTER_BOX_BW, int BHX = MVSTER_BOX_BHX, int NBUFS = MVSTER_BOX_NBUF>
 struct BoxCfg {
     static constexpr int TB = C * ES;                                    // texel bytes: 16, 32 or 64
-    static constexpr int LD = (TB == 64 && D % 4 == 0) ? 2 : 1;          // lanes per pixel (each owns D/LD hypotheses)
+#ifndef MVSTER_BOX_LD2_C16
+#define MVSTER_BOX_LD2_C16 0
+#endif
+    // lanes per pixel (each owns D/LD hypotheses): 2 for 64-byte texels (and, optionally, for every 16-channel texel)
+    static constexpr int LD = ((TB == 64 || (MVSTER_BOX_LD2_C16 && C == 16)) && D % 4 == 0) ? 2 : 1;
     static constexpr int DL = D / LD;
     static constexpr int PPW = 32 / LD;                                  // pixels per warp
     static constexpr int WX = LD;                                        // warps side by side: the tile is 32 wide
@@ -467,8 +474,7 @@ __global__ void __launch_bounds__(BoxCfg<C, D, (int)sizeof(T)>::WARPS * 32, BoxC
     // ---- phase A: bounding box of every view's sample positions --------------------------------------------------
     // Along one pixel's epipolar line the position is a Moebius function of the depth, monotone between the extreme
     // hypotheses unless z changes sign in between - which poisons the box with a NaN (no fit -> exact direct path).
-#pragma unroll 1
-    for (int v = 0; v < Nsrc; ++v) {
+    auto reduce_view = [&](int v) {
         const PixelView pv = pixel_view(rt_s + v * 12, fxp, fyp);
         f32x2 sx, sy, pz;
         positions2(pv, hext, sx, sy, pz);
@@ -493,8 +499,7 @@ __global__ void __launch_bounds__(BoxCfg<C, D, (int)sizeof(T)>::WARPS * 32, BoxC
         wb.z = __reduce_max_sync(0xffffffffu, hix);
         wb.w = __reduce_max_sync(0xffffffffu, hiy);
         if (lane == 0) wbox[v * WARPS + warp] = wb;
-    }
-    __syncthreads();
+    };
 
     // ---- the plan: one lane of warp 0 per view combines the warp boxes, publishes the descriptor and requests the
     //      box (or, when it does not fit, completes the view's barrier by hand).  The other warps pick the descriptor
@@ -509,8 +514,7 @@ __global__ void __launch_bounds__(BoxCfg<C, D, (int)sizeof(T)>::WARPS * 32, BoxC
             mbar_arrive(bar);
         }
     };
-    if (warp == 0 && lane < Nsrc) {
-        const int v = lane;
+    auto plan_view = [&](int v) {  // one thread
         int4 bb = wbox[v * WARPS];
 #pragma unroll
         for (int w = 1; w < WARPS; ++w) {
@@ -526,7 +530,23 @@ __global__ void __launch_bounds__(BoxCfg<C, D, (int)sizeof(T)>::WARPS * 32, BoxC
                               __int_as_float(fit ? 1 : 0));
         org[v] = make_int2(bx, by);
         if (v < NBUF) request(v, fit, bx, by);
-    }
+    };
+#if MVSTER_BOX_SPLIT_A
+    // view 0 first: its box is in flight while the boxes of the other views are reduced (one more CTA barrier, but the
+    // TMA round trip of the first view is what every warp waits for next)
+    reduce_view(0);
+    __syncthreads();
+    if (tid == 0) plan_view(0);
+#pragma unroll 1
+    for (int v = 1; v < Nsrc; ++v) reduce_view(v);
+    __syncthreads();
+    if (warp == 0 && lane >= 1 && lane < Nsrc) plan_view(lane);
+#else
+#pragma unroll 1
+    for (int v = 0; v < Nsrc; ++v) reduce_view(v);
+    __syncthreads();
+    if (warp == 0 && lane < Nsrc) plan_view(lane);
+#endif
 
     f32x2 acc2[GPL][NP], wsum2[NP];
 #pragma unroll

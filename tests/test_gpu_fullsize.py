@@ -383,3 +383,20 @@ def test_filter_512x640_matches_the_lifted_reference():
     ok = np.isfinite(w4) & (np.abs(a4 - w4) < 1.0)          # a vote that flipped changes the average by whole millimetres
     assert ok.mean() > 0.999
     assert np.abs(a4[ok] - w4[ok]).max() < 2e-3
+
+
+@pytest.mark.parametrize("n,c,g,d", [(8, 8, 4, 4), (16, 8, 4, 4), (7, 16, 4, 4), (9, 8, 2, 8)])
+def test_k1_many_source_views_recycle_the_staging_buffers(n, c, g, d):
+    """More source views than staging buffers (3): every further view is requested after a CTA barrier into a recycled
+    buffer, with the mbarrier phase flipping - up to the ABI's maximum of 15 source views."""
+    h, w = 40, 72
+    feats = [syn.smooth_features(1, c, h, w, 300 + v) for v in range(n)]
+    proj = syn.proj_matrices(1, n, h * 8, w * 8, 3, step_rad=0.01)
+    inv = 1.0 / syn.smooth_depth_map(h // 2, w // 2, 4, 600, 760)[None]
+    half = np.float32(2e-6)
+    hypo = O.schedule_inverse_range_np((inv + half).astype(np.float32), (inv - half).astype(np.float32), d, h, w)
+    vol, wts = mv.epipolar_weights([f.to(DEV) for f in feats], torch.from_numpy(proj).to(DEV),
+                                   torch.from_numpy(hypo).to(DEV), g, 2.0)
+    ref64, w64, _ = O.epipolar_aggregate_np(feats[0].numpy(), [f.numpy() for f in feats[1:]], proj, hypo, g, 2.0)
+    assert np.abs(vol.cpu().numpy() - ref64).max() < 1e-4
+    assert np.abs(wts.cpu().numpy() - w64).max() < 1e-4
