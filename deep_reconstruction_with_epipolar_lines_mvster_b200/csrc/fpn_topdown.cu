@@ -33,7 +33,7 @@ struct TopDownParams {
     const float* lat;       // [B,CL,H,W]     planar: encoder map of this level
     const float* intra_in;  // nullable [B,64,H,W]: load the tile instead of computing it
     float* intra_out;       // nullable [B,64,H,W]
-    float* feat;            // NHWC [B,H,W,co_total]
+    void* feat;             // NHWC [B,H,W,co_total], fp32 or bf16 (the kernel's OutT)
     int B, H, W, co_total, co_off;
     float sy, sx;           // align_corners=True source scale (Hl-1)/(H-1), (Wl-1)/(W-1)
 };
@@ -67,7 +67,12 @@ __device__ __forceinline__ void topdown_conv_half(const TopDownParams<CL, CO>& p
 
 constexpr int kTdThreads = 256;
 
-template <int CL, int CO>
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low half), .y = hi
+    return *reinterpret_cast<const unsigned*>(&v);
+}
+
+template <int CL, int CO, typename OutT>
 __global__ void __launch_bounds__(kTdThreads, 2) fpn_topdown_kernel(const __grid_constant__ TopDownParams<CL, CO> p) {
     extern __shared__ float tile[];  // [64][kTdHH][kTdRS]
     const int tid = threadIdx.x;
@@ -179,15 +184,29 @@ __global__ void __launch_bounds__(kTdThreads, 2) fpn_topdown_kernel(const __grid
         if (gx + c >= W) break;
 #pragma unroll
         for (int co = 0; co < CO; ++co) acc[c][co] += red[(c * CO + co) * 128];
-        float* fp = p.feat + ((size_t)b * plane + (size_t)gy * W + gx + c) * p.co_total + p.co_off;
+        const size_t fo = ((size_t)b * plane + (size_t)gy * W + gx + c) * p.co_total + p.co_off;
+        if constexpr (sizeof(OutT) == 4) {
+            float* fp = static_cast<float*>(p.feat) + fo;
 #pragma unroll
-        for (int q = 0; q < CO; q += 4)
-            *reinterpret_cast<float4*>(fp + q) = make_float4(acc[c][q], acc[c][q + 1], acc[c][q + 2], acc[c][q + 3]);
+            for (int q = 0; q < CO; q += 4)
+                *reinterpret_cast<float4*>(fp + q) = make_float4(acc[c][q], acc[c][q + 1], acc[c][q + 2], acc[c][q + 3]);
+        } else {  // bf16 (round to nearest even, as torch's .to(bfloat16)): 8 channels = one 16-byte store
+            __nv_bfloat16* fp = static_cast<__nv_bfloat16*>(p.feat) + fo;
+#pragma unroll
+            for (int q = 0; q < CO; q += 8) {
+                uint4 v;
+                v.x = pack_bf16x2(acc[c][q], acc[c][q + 1]);
+                v.y = pack_bf16x2(acc[c][q + 2], acc[c][q + 3]);
+                v.z = pack_bf16x2(acc[c][q + 4], acc[c][q + 5]);
+                v.w = pack_bf16x2(acc[c][q + 6], acc[c][q + 7]);
+                *reinterpret_cast<uint4*>(fp + q) = v;
+            }
+        }
     }
 }
 
-template <int CL, int CO>
-static int launch_topdown(const float* prev, const float* lat, const float* intra_in, float* intra_out, float* feat,
+template <int CL, int CO, typename OutT>
+static int launch_topdown(const float* prev, const float* lat, const float* intra_in, float* intra_out, void* feat,
                           const float* w_out, const float* w_in, const float* b_in, int B, int H, int W, int co_total,
                           int co_off, cudaStream_t s) {
     static thread_local TopDownParams<CL, CO> p;
@@ -201,11 +220,11 @@ static int launch_topdown(const float* prev, const float* lat, const float* intr
     p.sy = H > 1 ? (float)(Hl - 1) / (float)(H - 1) : 0.f;  // ATen area_pixel_compute_scale, align_corners=True
     p.sx = W > 1 ? (float)(Wl - 1) / (float)(W - 1) : 0.f;
     static int attr_done[64] = {};  // largest size set per device
-    const int st = ensure_dynamic_smem_bytes(fpn_topdown_kernel<CL, CO>, kTdSmem, attr_done, "fpn_topdown: cudaFuncSetAttribute");
+    const int st = ensure_dynamic_smem_bytes(fpn_topdown_kernel<CL, CO, OutT>, kTdSmem, attr_done, "fpn_topdown: cudaFuncSetAttribute");
     if (st != MVSTER_OK) return st;
     dim3 grid((W + kTdTW - 1) / kTdTW, (H + kTdTH - 1) / kTdTH, B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "fpn_topdown: grid too large");
-    fpn_topdown_kernel<CL, CO><<<grid, kTdThreads, kTdSmem, s>>>(p);
+    fpn_topdown_kernel<CL, CO, OutT><<<grid, kTdThreads, kTdSmem, s>>>(p);
     count_launch();
     MVSTER_CHECK_LAUNCH("fpn_topdown launch");
     return MVSTER_OK;
@@ -215,22 +234,35 @@ static int launch_topdown(const float* prev, const float* lat, const float* intr
 
 using namespace mvster;
 
-extern "C" int mvster_fpn_topdown(const float* prev, const float* lat, const float* intra_in, float* intra_out,
-                                  float* feat, const float* w_out_host, const float* w_in_host, const float* b_in_host,
-                                  int B, int Clat, int Cout, int Cout_total, int co_off, int H, int W, void* stream) {
+extern "C" int mvster_fpn_topdown_ex(const float* prev, const float* lat, const float* intra_in, float* intra_out,
+                                     void* feat, int feat_dtype, const float* w_out_host, const float* w_in_host,
+                                     const float* b_in_host, int B, int Clat, int Cout, int Cout_total, int co_off,
+                                     int H, int W, void* stream) {
     if (!feat || !w_out_host || !w_in_host || !b_in_host) return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown: null pointer");
+    if (feat_dtype != MVSTER_F32 && feat_dtype != MVSTER_BF16) return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown: feat_dtype must be MVSTER_F32 or MVSTER_BF16");
     if (!intra_in && (!prev || !lat))
         return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown: need prev + lat (compute the tile) or intra_in (reload it)");
     if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown: H, W must be positive and even");
-    if (co_off < 0 || co_off + Cout > Cout_total || (co_off % 4) || (Cout_total % 4))
+    const int cal = feat_dtype == MVSTER_BF16 ? 8 : 4;  // 16-byte stores
+    if (co_off < 0 || co_off + Cout > Cout_total || (co_off % cal) || (Cout_total % cal))
         return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown: bad output channel slice");
     if (((uintptr_t)feat) % 16) return fail(MVSTER_ERR_ALIGN, "fpn_topdown: feat must be 16-byte aligned");
     DeviceGuard guard(feat);
     if (guard.status != MVSTER_OK) return guard.status;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool bf = feat_dtype == MVSTER_BF16;
+#define MVSTER_TD_ARGS prev, lat, intra_in, intra_out, feat, w_out_host, w_in_host, b_in_host, B, H, W, Cout_total, co_off, s
     if (Clat == 8 && Cout == 8)
-        return launch_topdown<8, 8>(prev, lat, intra_in, intra_out, feat, w_out_host, w_in_host, b_in_host, B, H, W, Cout_total, co_off, s);
+        return bf ? launch_topdown<8, 8, __nv_bfloat16>(MVSTER_TD_ARGS) : launch_topdown<8, 8, float>(MVSTER_TD_ARGS);
     if (Clat == 16 && Cout == 8)
-        return launch_topdown<16, 8>(prev, lat, intra_in, intra_out, feat, w_out_host, w_in_host, b_in_host, B, H, W, Cout_total, co_off, s);
+        return bf ? launch_topdown<16, 8, __nv_bfloat16>(MVSTER_TD_ARGS) : launch_topdown<16, 8, float>(MVSTER_TD_ARGS);
+#undef MVSTER_TD_ARGS
     return fail(MVSTER_ERR_UNSUPPORTED, "fpn_topdown: no kernel for Clat=%d Cout=%d (built: (8,8), (16,8))", Clat, Cout);
+}
+
+extern "C" int mvster_fpn_topdown(const float* prev, const float* lat, const float* intra_in, float* intra_out,
+                                  float* feat, const float* w_out_host, const float* w_in_host, const float* b_in_host,
+                                  int B, int Clat, int Cout, int Cout_total, int co_off, int H, int W, void* stream) {
+    return mvster_fpn_topdown_ex(prev, lat, intra_in, intra_out, feat, MVSTER_F32, w_out_host, w_in_host, b_in_host, B,
+                                 Clat, Cout, Cout_total, co_off, H, W, stream);
 }

@@ -168,11 +168,15 @@ class FPN4(_FoldedWeights, nn.Module):
             self._fold_cache[tag + "@dev"] = hit
         return hit[1], hit[2]
 
-    def forward_direct(self, x) -> Dict[str, torch.Tensor]:
+    def forward_direct(self, x, feature_dtype: Optional[torch.dtype] = None) -> Dict[str, torch.Tensor]:
         """Eval-mode FPN4 on the B200 kernels: encoder levels 0-2 as direct convolutions (BatchNorm folded), level 3
         and the coarse top-down steps on cuDNN, the two finest top-down steps fused with their output convolutions
-        (``ops.fpn_topdown``).  Every output is NHWC in memory (``channels_last`` strides), ready for K1."""
+        (``ops.fpn_topdown``).  Every output is NHWC in memory (``channels_last`` strides), ready for K1.
+        ``feature_dtype=torch.bfloat16``: the four feature maps are EMITTED in bf16 (stages 3-4 by the top-down kernel's
+        epilogue, stages 1-2 by the planar -> NHWC transpose that the fp32 path runs as well) - K1 consumes them
+        zero-copy, there is no separate cast pass over the feature maps."""
         x = x.contiguous()
+        fdt = feature_dtype or torch.float32
         c0 = self._block(self.conv0[1], "c01", self._block(self.conv0[0], "c00", x))
         c1 = c0
         for i, blk in enumerate(self.conv1):
@@ -183,7 +187,7 @@ class FPN4(_FoldedWeights, nn.Module):
         top = c2
         for i, blk in enumerate(self.conv3):
             top = self._block(blk, "c3%d" % i, top)
-        out = {"stage1": self.out1(top).contiguous(memory_format=torch.channels_last)}
+        out = {"stage1": ops.to_nhwc(self.out1(top), fdt).permute(0, 3, 1, 2)}
         intra2 = self._up(top) + self.inner1(c2)
         if ops.conv3d_mid_supported(self.out2.in_channels, self.out2.out_channels, 1, intra2.shape[2], intra2.shape[3]):
             key = (self.out2.weight._version, self.out2.weight.data_ptr(), str(x.device))
@@ -195,11 +199,11 @@ class FPN4(_FoldedWeights, nn.Module):
             feat2 = ops.conv3d_mid(intra2.contiguous().unsqueeze(2), hit[1], hit[2], relu=False).squeeze(2)
         else:
             feat2 = self.out2(intra2)
-        out["stage2"] = feat2.contiguous(memory_format=torch.channels_last)
+        out["stage2"] = ops.to_nhwc(feat2, fdt).permute(0, 3, 1, 2)
         w3, wi3, bi3 = self._topdown_weights(self.out3, self.inner2, "td3")
-        feat3, intra3 = ops.fpn_topdown(intra2, c1, w3, wi3, bi3, want_intra=True)
+        feat3, intra3 = ops.fpn_topdown(intra2, c1, w3, wi3, bi3, want_intra=True, feature_dtype=fdt)
         w4, wi4, bi4 = self._topdown_weights(self.out4, self.inner3, "td4")
-        feat4, _ = ops.fpn_topdown(intra3, c0, w4, wi4, bi4, want_intra=False)
+        feat4, _ = ops.fpn_topdown(intra3, c0, w4, wi4, bi4, want_intra=False, feature_dtype=fdt)
         out["stage3"] = feat3.permute(0, 3, 1, 2)
         out["stage4"] = feat4.permute(0, 3, 1, 2)
         return out
@@ -435,7 +439,7 @@ class MVS4net(_FoldedWeights, nn.Module):
         b = imgs[0].shape[0]
         stacked = torch.cat(list(imgs), 0)
         if self.feature.direct_supported(stacked) and not torch.is_grad_enabled():
-            out = self.feature.forward_direct(stacked)
+            out = self.feature.forward_direct(stacked, self.stagenet.feature_dtype)
         else:
             out = self.feature(stacked.contiguous(memory_format=torch.channels_last))
         return [{k: v[i * b:(i + 1) * b] for k, v in out.items()} for i in range(n)]

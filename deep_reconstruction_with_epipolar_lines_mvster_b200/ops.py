@@ -420,19 +420,23 @@ def conv2d_small(x: torch.Tensor, w_slices: Sequence[torch.Tensor], b_slices: Se
 
 
 def fpn_topdown(prev: torch.Tensor, lat: torch.Tensor, w_out_slices: Sequence[torch.Tensor], w_in_host: torch.Tensor,
-                b_in_host: torch.Tensor, want_intra: bool):
+                b_in_host: torch.Tensor, want_intra: bool, feature_dtype: Optional[torch.dtype] = None):
     """One FPN4 top-down level (mvs4net_utils.py:488-495): ``intra = up2(prev) + inner(lat); feat = out_conv(intra)``.
     ``prev`` [B,64,H/2,W/2], ``lat`` [B,Clat,H,W] planar CUDA fp32; ``w_out_slices[i]`` [3,3,64,8] CPU.
     Returns ``(feat NHWC [B,H,W,8*len(slices)], intra [B,64,H,W] or None)``; ``intra`` is materialised only when asked
-    for or when a second output-channel slice has to reload it."""
+    for or when a second output-channel slice has to reload it.  ``feature_dtype=torch.bfloat16`` makes the kernel emit
+    the bf16 feature map K1 gathers from (rounded once from the fp32 accumulators; no cast pass)."""
     _require_cuda(prev, "prev")
+    feature_dtype = feature_dtype or torch.float32
+    if feature_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("fpn_topdown: feature dtype must be float32 or bfloat16")
     prev, lat = _f32c(prev, "prev"), _f32c(lat, "lat")
     b, clat, h, w = lat.shape
     if tuple(prev.shape) != (b, 64, h // 2, w // 2) or h % 2 or w % 2:
         raise RuntimeError("fpn_topdown: prev %s does not match lat %s" % (tuple(prev.shape), tuple(lat.shape)))
     ns = len(w_out_slices)
     cout = 8 * ns
-    feat = torch.empty((b, h, w, cout), device=lat.device, dtype=torch.float32)
+    feat = torch.empty((b, h, w, cout), device=lat.device, dtype=feature_dtype)
     intra = torch.empty((b, 64, h, w), device=lat.device, dtype=torch.float32) if (want_intra or ns > 1) else None
     lib = _lib.load()
     for t in (w_in_host, b_in_host) + tuple(w_out_slices):
@@ -444,9 +448,9 @@ def fpn_topdown(prev: torch.Tensor, lat: torch.Tensor, w_out_slices: Sequence[to
         if tuple(ws.shape) != (3, 3, 64, 8):
             raise RuntimeError("fpn_topdown: output-conv slices must be [3,3,64,8]")
         first = i == 0
-        _lib.check(lib.mvster_fpn_topdown(
+        _lib.check(lib.mvster_fpn_topdown_ex(
             _ptr(prev) if first else None, _ptr(lat) if first else None, None if first else _ptr(intra),
-            _ptr(intra) if first else None, _ptr(feat), ctypes.c_void_p(ws.data_ptr()),
+            _ptr(intra) if first else None, _ptr(feat), _dtype_code(feat), ctypes.c_void_p(ws.data_ptr()),
             ctypes.c_void_p(w_in_host.data_ptr()), ctypes.c_void_p(b_in_host.data_ptr()), b, clat, 8, cout, 8 * i, h, w,
             _stream(lat)))
     return feat, intra

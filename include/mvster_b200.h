@@ -203,6 +203,12 @@ int mvster_conv2d_small(const float* x, const float* w, const float* bias, float
 int mvster_fpn_topdown(const float* prev, const float* lat, const float* intra_in, float* intra_out, float* feat,
                        const float* w_out, const float* w_in, const float* b_in, int B, int Clat, int Cout,
                        int Cout_total, int co_off, int H, int W, void* stream);
+/* mvster_fpn_topdown_ex: the same level with a choice of the emitted feature type - feat_dtype MVSTER_F32 or
+ * MVSTER_BF16 (round to nearest even of the fp32 result; co_off and Cout_total then multiples of 8).  With MVSTER_BF16
+ * FPN4 (models/mvs4net_utils.py:426-509) hands K1 its bf16 NHWC feature maps directly, without a cast pass. */
+int mvster_fpn_topdown_ex(const float* prev, const float* lat, const float* intra_in, float* intra_out, void* feat,
+                          int feat_dtype, const float* w_out, const float* w_in, const float* b_in, int B, int Clat,
+                          int Cout, int Cout_total, int co_off, int H, int W, void* stream);
 /* backward of the tail w.r.t. the logits: softmax backward of g_attn (+ the regression term of g_depth when
  * depth_mode == MVSTER_DEPTH_REGRESS); g_attn / g_depth may be NULL (treated as zero) */
 int mvster_tail_bwd(const float* attn, const float* hypo, const float* depth, const float* g_attn,

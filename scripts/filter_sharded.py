@@ -41,7 +41,14 @@ def main():
     k = syn.intrinsics(h, w, 3)
     es = np.stack([syn.grid_extrinsics(i, 7, 0.04) for i in range(v)])
     ks = np.stack([k] * v)
-    depths = syn.render_surface_depths(k, list(es), h, w, noise_mm=0.3, seed=0)       # same scene on every rank
+    cache = "/tmp/mvster_filter_depths_%d.npy" % v                                    # 15 s of CPU rendering: once per box
+    if os.path.exists(cache):
+        depths = np.load(cache)
+    else:
+        depths = syn.render_surface_depths(k, list(es), h, w, noise_mm=0.3, seed=0)   # same scene on every rank
+        if rank == 0:
+            np.save(cache + ".tmp.npy", depths)
+            os.replace(cache + ".tmp.npy", cache)
     conf = np.random.RandomState(0).uniform(0, 1, size=(v, h, w)).astype(np.float32)
     pairs = np.concatenate([np.arange(v)[:, None], syn.pair_list(v, s)], 1).astype(np.int32)
     dz, cf = torch.from_numpy(depths).to(dev), torch.from_numpy(conf).to(dev)         # replicated stack

@@ -359,6 +359,62 @@ def test_fpn4_direct_path_matches_reference_golden(golden, model):
         assert np.abs(out[k].cpu().numpy() - ref).max() < 5e-5 * max(1.0, float(np.abs(ref).max())), k
 
 
+def test_fpn4_emits_bf16_feature_maps_directly(golden, model):
+    """§8f rank 2: FPN4 hands K1 bf16 NHWC feature maps without a cast pass.  The emitted values are the fp32 path's
+    values rounded once to nearest-even - bit-identical to ``fp32_output.to(bfloat16)``; tolerance against the
+    reference's fp32 golden: 2^-8 relative (bf16 has 8 significand bits), written here."""
+    g = golden("network")
+    x = torch.from_numpy(g["imgs"][1]).to(DEV)
+    launches0 = mv.launch_count()
+    with torch.no_grad():
+        out32 = model.feature.forward_direct(x)
+        n32 = mv.launch_count() - launches0
+        out16 = model.feature.forward_direct(x, torch.bfloat16)
+        n16 = mv.launch_count() - launches0 - n32
+    assert n16 == n32                                      # no extra pass of this library ...
+    for k in ("stage1", "stage2", "stage3", "stage4"):
+        assert out16[k].dtype == torch.bfloat16 and out16[k].is_contiguous(memory_format=torch.channels_last)
+        assert ops.to_nhwc(out16[k], torch.bfloat16).data_ptr() == out16[k].data_ptr()   # ... and K1 takes it zero-copy
+        assert torch.equal(out16[k], out32[k].to(torch.bfloat16)), k
+        ref = g["fpn_view1_" + k]
+        err = np.abs(out16[k].float().cpu().numpy() - ref)
+        assert (err <= 2.0 ** -8 * np.abs(ref) + 5e-5 * max(1.0, float(np.abs(ref).max()))).all(), k
+
+
+def test_fpn_topdown_bf16_slices_and_rejections():
+    rng = np.random.RandomState(5)
+    h, w = 12, 36
+    prev = torch.from_numpy(rng.normal(0, 1, (1, 64, h // 2, w // 2)).astype(np.float32)).to(DEV)
+    lat = torch.from_numpy(rng.normal(0, 1, (1, 16, h, w)).astype(np.float32)).to(DEV)
+    slices = [torch.from_numpy(rng.normal(0, 0.05, (3, 3, 64, 8)).astype(np.float32)) for _ in range(2)]
+    w_in, b_in = torch.from_numpy(rng.normal(0, 0.3, (16, 64)).astype(np.float32)), torch.zeros(64)
+    f32, _ = ops.fpn_topdown(prev, lat, slices, w_in, b_in, True)
+    f16, _ = ops.fpn_topdown(prev, lat, slices, w_in, b_in, True, feature_dtype=torch.bfloat16)
+    assert f16.dtype == torch.bfloat16 and torch.equal(f16, f32.to(torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        ops.fpn_topdown(prev, lat, slices, w_in, b_in, True, feature_dtype=torch.float16)
+
+
+def test_mvs4net_bf16_features_end_to_end(model):
+    """Whole network with bf16 feature maps emitted by FPN4 (fp32 accumulation in K1, fp32 everywhere else) against
+    the fp32 network on the same input: stage-1 attention within 2e-2 (bf16 features: 2^-9 relative rounding on 64
+    channels of O(1) values), final depth within one stage-4 hypothesis interval on > 99 % of the pixels."""
+    h0, w0, n = 64, 128, 3
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    proj = {k: torch.from_numpy(v).to(DEV) for k, v in syn.proj_matrices_all_stages(1, n, h0, w0).items()}
+    dv = torch.from_numpy(syn.depth_values(1)).to(DEV)
+    imgs = [torch.rand((1, 3, h0, w0), device=DEV, generator=gen) for _ in range(n)]
+    m16 = mv.MVS4net(**CFG, feature_dtype=torch.bfloat16).eval().to(DEV)
+    m16.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        want = model(imgs, proj, dv)
+        got = m16(imgs, proj, dv)
+    assert (got["stage1"]["attn_weight"] - want["stage1"]["attn_weight"]).abs().max().item() < 2e-2
+    d32, d16 = want["stage4"]["depth"], got["stage4"]["depth"]
+    itv = (want["stage4"]["hypo_depth"][:, 0] - want["stage4"]["hypo_depth"][:, 1]).abs()
+    assert ((d32 - d16).abs() <= itv * 1.001).float().mean().item() > 0.99
+
+
 def test_graphed_forward_equals_eager_forward(model):
     h0, w0, n = 64, 128, 3
     gen = torch.Generator(device=DEV).manual_seed(9)
