@@ -41,7 +41,11 @@ struct EpiBwdParams {
 
 constexpr int kBwdWarps = 4;
 
+#ifndef MVSTER_BWD_KO
+#define MVSTER_BWD_KO 0   // development only, WRONG RESULTS: 1 = no reduction reaches memory (the arithmetic stays alive)
+#endif
 __device__ __forceinline__ void red8(float* p, const float* v) {
+    if (MVSTER_BWD_KO && reinterpret_cast<uintptr_t>(p) != 1) return;
     red_add_v4(p, v[0], v[1], v[2], v[3]);
     red_add_v4(p + 4, v[4], v[5], v[6], v[7]);
 }
@@ -52,19 +56,34 @@ __device__ __forceinline__ void red8(float* p, const float* v) {
 #ifndef MVSTER_BWD_MINB8
 #define MVSTER_BWD_MINB8 3  // D = 8 (coarse stages): 168 registers + 16-48 bytes of spills at 12 warps per SM beat 248 registers at 8 (stage 2: 0.182 -> 0.152 ms)
 #endif
-template <int C, int CPG, int D, typename T>
-__global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : MVSTER_BWD_MINB)
+// Hypothesis split of the direct kernel: DS lanes share a pixel's channel chunk and each owns D / DS hypotheses.  At
+// the coarse stages (D = 8, 1/8 and 1/4 resolution) a launch is only a few waves of long serial per-lane chains
+// (32 samples x ~400 instructions) at 12 warps per SM; splitting halves the chain and the hypothesis-indexed register
+// arrays, so twice the warps run at a higher occupancy.  The softmax statistics and the reference gradient are
+// combined across the DS lanes with shuffles.
+#ifndef MVSTER_BWD_DSPLIT8
+#define MVSTER_BWD_DSPLIT8 2
+#endif
+#ifndef MVSTER_BWD_MINB_SPLIT
+#define MVSTER_BWD_MINB_SPLIT 4
+#endif
+template <int C, int CPG, int D, typename T, int DS>
+__global__ void __launch_bounds__(kBwdWarps * 32, DS > 1 ? MVSTER_BWD_MINB_SPLIT : ((D > 4) ? MVSTER_BWD_MINB8 : MVSTER_BWD_MINB))
     epi_bwd_kernel(const __grid_constant__ EpiBwdParams p) {
     constexpr int CPL = 8;
-    constexpr int L = C / CPL;
+    constexpr int L = C / CPL;        // lanes per channel sweep
+    constexpr int LP = L * DS;        // lanes per pixel
+    constexpr int DL = D / DS;        // hypotheses per lane
     constexpr int GPL = CPL / CPG;
-    constexpr int PPW = 32 / L;
+    constexpr int PPW = 32 / LP;
     constexpr int G = C / CPG;
+    static_assert(D % DS == 0 && LP <= 32, "bad hypothesis split");
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane % L;
-    const int pix = lane / L;
+    const int ds = (lane / L) % DS;
+    const int pix = lane / LP;
     const int b = blockIdx.z;
     int x = blockIdx.x * PPW + pix;
     int y = blockIdx.y * kBwdWarps + warp;
@@ -82,15 +101,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : M
 #pragma unroll
     for (int c = 0; c < CPL; ++c) gref[c] = 0.0f;
 
-    float hyp[D], dS[D], dA[GPL][D];
+    float hyp[DL], dS[DL], dA[GPL][DL];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-        hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + d) * plane + pix_off);
-        const float inv_s = 1.0f / ldg_stream(p.wsum + ((size_t)b * D + d) * plane + pix_off);
+    for (int d = 0; d < DL; ++d) {
+        const int dg = ds * DL + d;
+        hyp[d] = ldg_stream(p.hypo + ((size_t)b * D + dg) * plane + pix_off);
+        const float inv_s = 1.0f / ldg_stream(p.wsum + ((size_t)b * D + dg) * plane + pix_off);
         float part = 0.0f;
 #pragma unroll
         for (int g = 0; g < GPL; ++g) {
-            const size_t o = (((size_t)b * G + sub * GPL + g) * D + d) * plane + pix_off;
+            const size_t o = (((size_t)b * G + sub * GPL + g) * D + dg) * plane + pix_off;
             const float go = live ? ldg_stream(p.gout + o) : 0.0f;  // dead lanes contribute nothing
             const float ov = ldg_stream(p.out + o);
             dA[g][d] = go * inv_s;
@@ -116,11 +136,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : M
         const float az = fmaf(h.r20, fx, fmaf(h.r21, fy, h.r22));
 
         // ---- pass A: recompute warped features, correlations, attention --------------------------------------
-        float wv[D][CPL];
-        float cor[GPL][D];
-        float score[D], dw[D];
+        float wv[DL][CPL];
+        float cor[GPL][DL];
+        float score[DL], dw[DL];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
+        for (int d = 0; d < DL; ++d) {
             const Taps t = make_taps(ax, ay, az, h, hyp[d], p.Hs, p.Ws);
 #pragma unroll
             for (int c = 0; c < CPL; ++c) wv[d][c] = 0.0f;
@@ -149,32 +169,38 @@ __global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : M
 #pragma unroll
         for (int m = 1; m < L; m <<= 1) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
+            for (int d = 0; d < DL; ++d) {
                 score[d] += __shfl_xor_sync(0xffffffffu, score[d], m);
                 dw[d] += __shfl_xor_sync(0xffffffffu, dw[d], m);
             }
         }
         float mx = score[0];
 #pragma unroll
-        for (int d = 1; d < D; ++d) mx = fmaxf(mx, score[d]);
-        float pr[D], es = 0.0f;
+        for (int d = 1; d < DL; ++d) mx = fmaxf(mx, score[d]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
+        for (int m = L; m < LP; m <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        float pr[DL], es = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DL; ++d) {
             pr[d] = exp2f((score[d] - mx) * p.score_scale);
             es += pr[d];
         }
+#pragma unroll
+        for (int m = L; m < LP; m <<= 1) es += __shfl_xor_sync(0xffffffffu, es, m);
         const float inv_es = 1.0f / es;
         float dot = 0.0f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
+        for (int d = 0; d < DL; ++d) {
             pr[d] *= inv_es;
             dw[d] = (dw[d] + dS[d]) * p.inv_sqrt_c;  // dp[d]
             dot = fmaf(pr[d], dw[d], dot);
         }
+#pragma unroll
+        for (int m = L; m < LP; m <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
 
         // ---- pass B: gradients, scatter ----------------------------------------------------------------------
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
+        for (int d = 0; d < DL; ++d) {
             const float dscore = p.inv_temp * pr[d] * (dw[d] - dot);
             const float w = pr[d] * p.inv_sqrt_c;
             float dwarp[CPL];
@@ -192,16 +218,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : M
             // active taps: non-zero weight (implies in-bounds) on a live lane
             const float wl0 = live ? t.w00 : 0.0f, wr0 = live ? t.w01 : 0.0f;
             const float wl1 = live ? t.w10 : 0.0f, wr1 = live ? t.w11 : 0.0f;
-            // neighbour exchange: lane+L is the next pixel (same channel chunk); hand my right column to it when
+            // neighbour exchange: lane+LP is the next pixel (same channel chunk, same hypotheses); hand my right column to it when
             // it is that lane's active left column, and take the previous pixel's right column likewise.
-            const int nxt_ol0 = __shfl_down_sync(0xffffffffu, t.o00, L);
-            const int nxt_ol1 = __shfl_down_sync(0xffffffffu, t.o10, L);
-            const float nxt_wl0 = __shfl_down_sync(0xffffffffu, wl0, L);
-            const float nxt_wl1 = __shfl_down_sync(0xffffffffu, wl1, L);
-            const int prv_or0 = __shfl_up_sync(0xffffffffu, t.o01, L);
-            const int prv_or1 = __shfl_up_sync(0xffffffffu, t.o11, L);
-            const float prv_wr0 = __shfl_up_sync(0xffffffffu, wr0, L);
-            const float prv_wr1 = __shfl_up_sync(0xffffffffu, wr1, L);
+            const int nxt_ol0 = __shfl_down_sync(0xffffffffu, t.o00, LP);
+            const int nxt_ol1 = __shfl_down_sync(0xffffffffu, t.o10, LP);
+            const float nxt_wl0 = __shfl_down_sync(0xffffffffu, wl0, LP);
+            const float nxt_wl1 = __shfl_down_sync(0xffffffffu, wl1, LP);
+            const int prv_or0 = __shfl_up_sync(0xffffffffu, t.o01, LP);
+            const int prv_or1 = __shfl_up_sync(0xffffffffu, t.o11, LP);
+            const float prv_wr0 = __shfl_up_sync(0xffffffffu, wr0, LP);
+            const float prv_wr1 = __shfl_up_sync(0xffffffffu, wr1, LP);
             const bool give0 = has_next && wr0 != 0.0f && nxt_wl0 != 0.0f && nxt_ol0 == t.o01;
             const bool give1 = has_next && wr1 != 0.0f && nxt_wl1 != 0.0f && nxt_ol1 == t.o11;
             const bool take0 = has_prev && prv_wr0 != 0.0f && wl0 != 0.0f && prv_or0 == t.o00;
@@ -210,7 +236,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : M
             float left0[CPL], left1[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                const float prv = __shfl_up_sync(0xffffffffu, dwarp[c], L);
+                const float prv = __shfl_up_sync(0xffffffffu, dwarp[c], LP);
                 left0[c] = fmaf(wl0, dwarp[c], tk0 * prv);
                 left1[c] = fmaf(wl1, dwarp[c], tk1 * prv);
             }
@@ -231,7 +257,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, (D > 4) ? MVSTER_BWD_MINB8 : M
         }
     }
 
-    if (live) {
+#pragma unroll
+    for (int m = L; m < LP; m <<= 1)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) gref[c] += __shfl_xor_sync(0xffffffffu, gref[c], m);
+    if (live && ds == 0) {
         float* gp = p.grad_ref + (((size_t)b * plane + pix_off) * C + sub * CPL);
         float4* g4 = reinterpret_cast<float4*>(gp);
         g4[0] = make_float4(gref[0], gref[1], gref[2], gref[3]);
@@ -628,10 +658,11 @@ static int try_bwd_tma(const EpiBwdParams& p, int cpg, int D, cudaStream_t s) {
 
 template <int C, int CPG, int D, typename T>
 static int launch_bwd(const EpiBwdParams& p, cudaStream_t stream) {
-    constexpr int PPW = 32 / (C / 8);
+    constexpr int DS = (D == 8) ? MVSTER_BWD_DSPLIT8 : 1;
+    constexpr int PPW = 32 / ((C / 8) * DS);
     dim3 grid((p.W + PPW - 1) / PPW, (p.H + kBwdWarps - 1) / kBwdWarps, p.B);
     if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "epi_bwd: grid too large");
-    epi_bwd_kernel<C, CPG, D, T><<<grid, kBwdWarps * 32, 0, stream>>>(p);
+    epi_bwd_kernel<C, CPG, D, T, DS><<<grid, kBwdWarps * 32, 0, stream>>>(p);
     count_launch();
     MVSTER_CHECK_LAUNCH("epi_bwd launch");
     return MVSTER_OK;

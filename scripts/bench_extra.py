@@ -123,10 +123,25 @@ def bench_train(args, dev):
             rt = ops.compose_homographies(proj)
             vol, wsum, _ = ops.epi_fwd(nh[0], nh[1:], rt, hypo, g, 2.0, want_wsum=True)
             ms = timed(lambda: ops.epi_bwd(nh[0], nh[1:], rt, hypo, vol, wsum, gout, g, 2.0), args.iters)
+            # the same call replayed from a CUDA graph (10 calls per replay): device time without the Python / ctypes
+            # / allocator cost of an eager call, which exceeds the kernel time at the coarse stages
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                ops.epi_bwd(nh[0], nh[1:], rt, hypo, vol, wsum, gout, g, 2.0)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(10):
+                    keep = ops.epi_bwd(nh[0], nh[1:], rt, hypo, vol, wsum, gout, g, 2.0)
+            gms = timed(graph.replay, max(3, args.iters // 4)) / 10
+            del graph, keep
         px = 2 * h * w
         alg = px * (4 * g * d * 2 + 4 * d * 2 + 5 * c * 4 * 2)
         out["stage%d_bwd_call_ms" % (stage + 1)] = ms
         out["stage%d_bwd_frac_hbm_roofline" % (stage + 1)] = alg / (HBM * 1e6) / ms
+        out["stage%d_bwd_graph_ms" % (stage + 1)] = gms
+        out["stage%d_bwd_graph_frac_hbm_roofline" % (stage + 1)] = alg / (HBM * 1e6) / gms
     out["bench"] = "train_k1_fwd_bwd"
     out["config"] = "512x640 B=2 N=5 fp32, EpipolarAggregate autograd (includes layout views, zero-init of grads)"
     print(json.dumps(out))
