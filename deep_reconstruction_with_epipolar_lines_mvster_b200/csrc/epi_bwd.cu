@@ -289,6 +289,11 @@ struct EpiBwdTmaParams {
 #define MVSTER_BWD_TMA_MINB(C) ((C) == 8 ? 4 : 3)
 #endif
 
+// neighbour-lane merge of the right tap column in the TMA kernel (1 = on)
+#ifndef MVSTER_BWD_TMA_NBR
+#define MVSTER_BWD_TMA_NBR 1
+#endif
+
 template <int C, int CPG, int D>
 __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB(C))
     epi_bwd_tma_kernel(const __grid_constant__ EpiBwdTmaParams pp) {
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB(C))
             const float wl0 = gx * gy, wr0 = hx * gy, wl1 = gx * hy, wr1 = hx * hy;
             // texel offsets (compared between lanes only where the weight is non-zero, i.e. in bounds)
             const int o00 = y0 * p.Ws + x0, o01 = o00 + 1, o10 = o00 + p.Ws, o11 = o10 + 1;
+#if MVSTER_BWD_TMA_NBR
             const int nxt_ol0 = __shfl_down_sync(0xffffffffu, o00, L);
             const int nxt_ol1 = __shfl_down_sync(0xffffffffu, o10, L);
             const float nxt_wl0 = __shfl_down_sync(0xffffffffu, wl0, L);
@@ -582,6 +588,9 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB(C))
             const bool take1 = has_prev && prv_wr1 != 0.0f && wl1 != 0.0f && prv_or1 == o10;
             const float tk0 = take0 ? prv_wr0 : 0.0f, tk1 = take1 ? prv_wr1 : 0.0f;
             const float kr0 = give0 ? 0.0f : wr0, kr1 = give1 ? 0.0f : wr1;  // right-column weights kept by this lane
+#else
+            const float kr0 = wr0, kr1 = wr1;
+#endif
             if (d > 0 && (x0 != px0 || y0 != py0)) {
                 flush();
                 fL0 = fL1 = fR0 = fR1 = false;
@@ -589,15 +598,23 @@ __global__ void __launch_bounds__(128, MVSTER_BWD_TMA_MINB(C))
                 for (int q = 0; q < 4; ++q) aL0[q] = aL1[q] = aR0[q] = aR1[q] = pack2(0.0f, 0.0f);
             }
             px0 = x0; py0 = y0;
-            const f32x2 pl0 = pack2(wl0, wl0), pl1 = pack2(wl1, wl1), pt0 = pack2(tk0, tk0), pt1 = pack2(tk1, tk1);
+            const f32x2 pl0 = pack2(wl0, wl0), pl1 = pack2(wl1, wl1);
             const f32x2 pr0 = pack2(kr0, kr0), pr1 = pack2(kr1, kr1);
+#if MVSTER_BWD_TMA_NBR
+            const f32x2 pt0 = pack2(tk0, tk0), pt1 = pack2(tk1, tk1);
+#endif
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+#if MVSTER_BWD_TMA_NBR
                 float lo, hi;
                 unpack2(dwp[q], lo, hi);
                 const f32x2 prv = pack2(__shfl_up_sync(0xffffffffu, lo, L), __shfl_up_sync(0xffffffffu, hi, L));
                 aL0[q] = fma2(pl0, dwp[q], fma2(pt0, prv, aL0[q]));
                 aL1[q] = fma2(pl1, dwp[q], fma2(pt1, prv, aL1[q]));
+#else
+                aL0[q] = fma2(pl0, dwp[q], aL0[q]);
+                aL1[q] = fma2(pl1, dwp[q], aL1[q]);
+#endif
                 aR0[q] = fma2(pr0, dwp[q], aR0[q]);
                 aR1[q] = fma2(pr1, dwp[q], aR1[q]);
             }

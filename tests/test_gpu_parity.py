@@ -340,6 +340,25 @@ def test_filter_fusion_matches_reference(golden):
     assert torch.equal(p2[1:], photo[1:]) and torch.equal(g2[1:], geo[1:]) and torch.equal(a2[1:], avg[1:])
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_filter_sharded_over_reference_views_equals_the_whole_scene(golden, world):
+    """SURVEY 8e for K2b: reference views dealt round-robin (``shard_pairs``), depth stack replicated - the rows every
+    rank computes are bit-identical to the same rows of the unsharded launch (ranks without a row stay idle)."""
+    g = golden("filter")
+    cfg = mv.FilterConfig(float(g["condmask_pixel"]), float(g["condmask_depth"]), float(g["photomask"]), int(g["geomask"]))
+    whole = mv.filter_scene(g["depths"], g["conf"], g["ks"], g["es"], g["pairs"], cfg, want_geo_sum=True)
+    seen = []
+    for rank in range(world):
+        rows, idx = mv.shard_pairs(list(g["pairs"]), rank, world)
+        seen += idx
+        if not rows:
+            continue
+        part = mv.filter_scene(g["depths"], g["conf"], g["ks"], g["es"], np.stack(rows), cfg, want_geo_sum=True)
+        for a, b in zip(part, whole):
+            assert torch.equal(a, b[idx])
+    assert sorted(seen) == list(range(len(g["pairs"])))
+
+
 def test_filter_same_camera_is_identity():
     h, w = 40, 56
     k = syn.intrinsics(h, w, 3)
