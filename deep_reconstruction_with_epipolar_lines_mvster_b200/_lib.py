@@ -37,6 +37,8 @@ _SIGNATURES = {
     "mvster_conv2d_mid5": (c_int, [_P, _P, _P, _P] + [c_int] * 6 + [_P]),
     "mvster_conv3d_mid": (c_int, [_P, _P, _P, _P] + [c_int] * 8 + [_P]),
     "mvster_conv2d_small": (c_int, [_P, _P, _P, _P] + [c_int] * 10 + [_P]),
+    "mvster_conv3d_mid_tc": (c_int, [_P, _P, _P, _P, _P] + [c_int] * 8 + [_P]),
+    "mvster_tf32_split": (c_int, [_P, _P, _P, ctypes.c_longlong, _P]),
     "mvster_fpn_topdown": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),
     "mvster_fpn_topdown_ex": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, _P] + [c_int] * 7 + [_P]),
     "mvster_tail_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),

@@ -7,6 +7,8 @@ no CPU path.
 from __future__ import annotations
 
 import ctypes
+import os
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -368,9 +370,37 @@ def conv3d_mid_supported(cin: int, cout: int, kd: int, h: int, w: int) -> bool:
     return cin in (32, 64) and cout % 16 == 0 and kd in (1, 3) and h % 2 == 0 and w % 2 == 0
 
 
-def conv3d_mid(x: torch.Tensor, w_dev: torch.Tensor, bias_dev: torch.Tensor, relu: bool = True) -> torch.Tensor:
-    """Direct fp32 stride-1 convolution of a 32/64-channel NCDHW volume with folded weights resident on the device
-    (reg2d conv4 / conv6, FPN4 conv3.1 / conv3.2 with D = 1).  ``w_dev`` [kd,3,3,Cin,Cout], ``bias_dev`` [Cout]."""
+_TC_SHAPES = {(1, 32, 32), (1, 64, 64), (1, 64, 32), (3, 32, 32), (3, 64, 64)}  # (kd, Cin, Cout) of mvster_conv3d_mid_tc
+_TF32_SPLIT_CACHE: dict = {}   # id(weight tensor) -> (weakref, version, hi, lo)
+
+
+def conv3d_mid_tc_enabled() -> bool:
+    """Tensor-core (3xTF32) kernels for the 32/64-channel layers; ``MVSTER_MID_TC=0`` selects the FP32 SIMT kernels."""
+    return os.environ.get("MVSTER_MID_TC", "1") != "0"
+
+
+def tf32_split(w_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(hi, lo)`` with ``hi = rna_tf32(w)``, ``lo = rna_tf32(w - hi)``, cached per weight tensor and version."""
+    _require_cuda(w_dev, "w_dev")
+    key = id(w_dev)
+    hit = _TF32_SPLIT_CACHE.get(key)
+    if hit is not None and hit[0]() is w_dev and hit[1] == w_dev._version:
+        return hit[2], hit[3]
+    hi, lo = torch.empty_like(w_dev), torch.empty_like(w_dev)
+    _lib.check(_lib.load().mvster_tf32_split(_ptr(w_dev), _ptr(hi), _ptr(lo), w_dev.numel(), _stream(w_dev)))
+    if len(_TF32_SPLIT_CACHE) > 256:
+        for k in [k for k, v in _TF32_SPLIT_CACHE.items() if v[0]() is None]:
+            del _TF32_SPLIT_CACHE[k]
+    _TF32_SPLIT_CACHE[key] = (weakref.ref(w_dev), w_dev._version, hi, lo)
+    return hi, lo
+
+
+def conv3d_mid(x: torch.Tensor, w_dev: torch.Tensor, bias_dev: torch.Tensor, relu: bool = True,
+               tensor_cores: Optional[bool] = None) -> torch.Tensor:
+    """fp32 stride-1 convolution of a 32/64-channel NCDHW volume with folded weights resident on the device
+    (reg2d conv4 / conv6, FPN4 conv3.1 / conv3.2 / out2 with D = 1).  ``w_dev`` [kd,3,3,Cin,Cout], ``bias_dev`` [Cout].
+    Shapes compiled for ``mvster_conv3d_mid_tc`` run as 3xTF32 implicit GEMMs on the tensor cores (fp32-grade accuracy;
+    ``tensor_cores=False`` or ``MVSTER_MID_TC=0``: the FP32 SIMT kernel), the others on the SIMT kernel (even H, W)."""
     x = _f32c(x, "x")
     _require_cuda(w_dev, "w_dev")
     _require_cuda(bias_dev, "bias_dev")
@@ -382,6 +412,12 @@ def conv3d_mid(x: torch.Tensor, w_dev: torch.Tensor, bias_dev: torch.Tensor, rel
     if wci != cin or bias_dev.numel() != cout:
         raise RuntimeError("conv3d_mid: weight %s does not match input channels %d" % (tuple(w_dev.shape), cin))
     y = torch.empty((b, cout, d, h, w), device=x.device, dtype=torch.float32)
+    use_tc = conv3d_mid_tc_enabled() if tensor_cores is None else bool(tensor_cores)
+    if use_tc and (int(kd), cin, cout) in _TC_SHAPES:
+        hi, lo = tf32_split(w_dev)
+        _lib.check(_lib.load().mvster_conv3d_mid_tc(_ptr(x), _ptr(hi), _ptr(lo), _ptr(bias_dev), _ptr(y), b, cin, cout, d, h,
+                                                    w, int(kd), int(bool(relu)), _stream(x)))
+        return y
     _lib.check(_lib.load().mvster_conv3d_mid(_ptr(x), _ptr(w_dev), _ptr(bias_dev), _ptr(y), b, cin, cout, d, h, w, int(kd),
                                              int(bool(relu)), _stream(x)))
     return y

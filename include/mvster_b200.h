@@ -189,6 +189,15 @@ int mvster_conv3d_mid(const float* x, const float* w_dev, const float* bias_dev,
  */
 int mvster_conv2d_small(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
                         int Cout_total, int co_off, int H, int W, int ksize, int stride, int relu, void* stream);
+/* mvster_conv3d_mid_tc: the same 32/64-channel stride-1 layers as mvster_conv3d_mid (reg2d conv4 / conv6,
+ * models/mvs4net_utils.py:896-903; FPN4 conv3.1 / conv3.2 / out2, :456-468) as an implicit GEMM on the tensor cores
+ * with fp32-grade accuracy: operands split into two TF32 numbers each, products accumulated as lo*hi + hi*lo + hi*hi
+ * in fp32 (3xTF32).  w_hi / w_lo dev [kd,3,3,Cin,Cout] are made once per layer by mvster_tf32_split from the folded
+ * fp32 weights.  Compiled (kd, Cin, Cout): (1,32,32) (1,64,64) (1,64,32) (3,32,32) (3,64,64); any H, W. */
+int mvster_conv3d_mid_tc(const float* x, const float* w_hi, const float* w_lo, const float* bias, float* y, int B,
+                         int Cin, int Cout, int D, int H, int W, int kd, int relu, void* stream);
+/* hi[i] = rna_tf32(w[i]), lo[i] = rna_tf32(w[i] - hi[i]) for n device floats */
+int mvster_tf32_split(const float* w, float* hi, float* lo, long long n, void* stream);
 /* mvster_fpn_topdown: one pyramid level of FPN4.forward (models/mvs4net_utils.py:488-495),
  *     intra = interpolate(prev, x2, bilinear, align_corners=True) + inner(lat);  feat = out_conv(intra)
  * with the 64-channel intra tile kept in shared memory; feat is written NHWC (what mvster_epi_fwd reads).
