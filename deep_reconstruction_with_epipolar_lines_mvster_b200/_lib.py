@@ -38,6 +38,8 @@ _SIGNATURES = {
     "mvster_conv3d_mid": (c_int, [_P, _P, _P, _P] + [c_int] * 8 + [_P]),
     "mvster_conv2d_small": (c_int, [_P, _P, _P, _P] + [c_int] * 10 + [_P]),
     "mvster_conv3d_mid_tc": (c_int, [_P, _P, _P, _P, _P] + [c_int] * 8 + [_P]),
+    "mvster_conv3d_mid_umma": (c_int, [_P, _P, _P, _P] + [c_int] * 8 + [_P]),
+    "mvster_umma_pack_weights": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "mvster_tf32_split": (c_int, [_P, _P, _P, ctypes.c_longlong, _P]),
     "mvster_fpn_topdown": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P] + [c_int] * 7 + [_P]),
     "mvster_fpn_topdown_ex": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, _P] + [c_int] * 7 + [_P]),

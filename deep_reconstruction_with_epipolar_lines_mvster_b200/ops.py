@@ -374,9 +374,33 @@ _TC_SHAPES = {(1, 32, 32), (1, 64, 64), (1, 64, 32), (3, 32, 32), (3, 64, 64)}  
 _TF32_SPLIT_CACHE: dict = {}   # id(weight tensor) -> (weakref, version, hi, lo)
 
 
+def conv3d_mid_tc_mode() -> int:
+    """Kernel family of the 32/64-channel layers (``MVSTER_MID_TC``): 2 = tcgen05 (UMMA, tensor memory), 1 = mma.sync,
+    0 = FP32 SIMT.  All three are fp32-grade (the tensor-core ones by a 3xTF32 operand split)."""
+    return int(os.environ.get("MVSTER_MID_TC", "2"))
+
+
 def conv3d_mid_tc_enabled() -> bool:
-    """Tensor-core (3xTF32) kernels for the 32/64-channel layers; ``MVSTER_MID_TC=0`` selects the FP32 SIMT kernels."""
-    return os.environ.get("MVSTER_MID_TC", "1") != "0"
+    return conv3d_mid_tc_mode() != 0
+
+
+_UMMA_PACK_CACHE: dict = {}   # id(weight tensor) -> (weakref, version, packed)
+
+
+def umma_pack_weights(w_dev: torch.Tensor) -> torch.Tensor:
+    """Folded weights [kd,3,3,Cin,Cout] -> the per-chunk hi / lo blocks ``mvster_conv3d_mid_umma`` copies in bulk."""
+    _require_cuda(w_dev, "w_dev")
+    hit = _UMMA_PACK_CACHE.get(id(w_dev))
+    if hit is not None and hit[0]() is w_dev and hit[1] == w_dev._version:
+        return hit[2]
+    kd, _, _, cin, cout = w_dev.shape
+    packed = torch.empty(2 * w_dev.numel(), device=w_dev.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_umma_pack_weights(_ptr(w_dev), _ptr(packed), int(kd), int(cin), int(cout), _stream(w_dev)))
+    if len(_UMMA_PACK_CACHE) > 256:
+        for k in [k for k, v in _UMMA_PACK_CACHE.items() if v[0]() is None]:
+            del _UMMA_PACK_CACHE[k]
+    _UMMA_PACK_CACHE[id(w_dev)] = (weakref.ref(w_dev), w_dev._version, packed)
+    return packed
 
 
 def tf32_split(w_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -396,7 +420,7 @@ def tf32_split(w_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def conv3d_mid(x: torch.Tensor, w_dev: torch.Tensor, bias_dev: torch.Tensor, relu: bool = True,
-               tensor_cores: Optional[bool] = None) -> torch.Tensor:
+               tensor_cores=None) -> torch.Tensor:
     """fp32 stride-1 convolution of a 32/64-channel NCDHW volume with folded weights resident on the device
     (reg2d conv4 / conv6, FPN4 conv3.1 / conv3.2 / out2 with D = 1).  ``w_dev`` [kd,3,3,Cin,Cout], ``bias_dev`` [Cout].
     Shapes compiled for ``mvster_conv3d_mid_tc`` run as 3xTF32 implicit GEMMs on the tensor cores (fp32-grade accuracy;
@@ -412,8 +436,13 @@ def conv3d_mid(x: torch.Tensor, w_dev: torch.Tensor, bias_dev: torch.Tensor, rel
     if wci != cin or bias_dev.numel() != cout:
         raise RuntimeError("conv3d_mid: weight %s does not match input channels %d" % (tuple(w_dev.shape), cin))
     y = torch.empty((b, cout, d, h, w), device=x.device, dtype=torch.float32)
-    use_tc = conv3d_mid_tc_enabled() if tensor_cores is None else bool(tensor_cores)
-    if use_tc and (int(kd), cin, cout) in _TC_SHAPES:
+    mode = conv3d_mid_tc_mode() if tensor_cores is None else int(tensor_cores)   # 0 SIMT, 1 / True mma.sync, 2 tcgen05
+    if mode == 2 and (int(kd), cin, cout) in _TC_SHAPES:
+        packed = umma_pack_weights(w_dev)
+        _lib.check(_lib.load().mvster_conv3d_mid_umma(_ptr(x), _ptr(packed), _ptr(bias_dev), _ptr(y), b, cin, cout, d, h, w,
+                                                      int(kd), int(bool(relu)), _stream(x)))
+        return y
+    if mode == 1 and (int(kd), cin, cout) in _TC_SHAPES:
         hi, lo = tf32_split(w_dev)
         _lib.check(_lib.load().mvster_conv3d_mid_tc(_ptr(x), _ptr(hi), _ptr(lo), _ptr(bias_dev), _ptr(y), b, cin, cout, d, h,
                                                     w, int(kd), int(bool(relu)), _stream(x)))

@@ -198,6 +198,13 @@ int mvster_conv3d_mid_tc(const float* x, const float* w_hi, const float* w_lo, c
                          int Cin, int Cout, int D, int H, int W, int kd, int relu, void* stream);
 /* hi[i] = rna_tf32(w[i]), lo[i] = rna_tf32(w[i] - hi[i]) for n device floats */
 int mvster_tf32_split(const float* w, float* hi, float* lo, long long n, void* stream);
+/* mvster_conv3d_mid_umma: the same layers on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
+ * tensor memory, 3xTF32 operand split, four round-robin accumulators against the accumulator's truncation).
+ * w_packed is made once per layer by mvster_umma_pack_weights from the folded fp32 weights [kd,3,3,Cin,Cout]
+ * (same number of floats x 2).  Compiled (kd, Cin, Cout): (1,32,32) (1,64,64) (1,64,32) (3,32,32) (3,64,64); any H, W. */
+int mvster_conv3d_mid_umma(const float* x, const float* w_packed, const float* bias, float* y, int B, int Cin, int Cout,
+                           int D, int H, int W, int kd, int relu, void* stream);
+int mvster_umma_pack_weights(const float* w, float* packed, int kd, int Cin, int Cout, void* stream);
 /* mvster_fpn_topdown: one pyramid level of FPN4.forward (models/mvs4net_utils.py:488-495),
  *     intra = interpolate(prev, x2, bilinear, align_corners=True) + inner(lat);  feat = out_conv(intra)
  * with the 64-channel intra tile kept in shared memory; feat is written NHWC (what mvster_epi_fwd reads).

@@ -203,7 +203,7 @@ def test_conv3d_mid_matches_float64_torch(cin, cout, kd, d, h, w):
     bias = rng.normal(0, 0.3, cout).astype(np.float32)
     ref = F.conv3d(torch.from_numpy(x).double(), torch.from_numpy(wt).double().permute(4, 3, 0, 1, 2), padding=(kd // 2, 1, 1))
     ref = torch.relu(ref + torch.from_numpy(bias).double().view(1, -1, 1, 1, 1))
-    for tc in (False, True):   # the FP32 SIMT kernel and (where compiled for the shape) the 3xTF32 tensor-core kernel
+    for tc in (0, 1, 2):   # the FP32 SIMT kernel and (where compiled for the shape) the 3xTF32 mma.sync / tcgen05 kernels
         got = ops.conv3d_mid(torch.from_numpy(x).to(DEV), torch.from_numpy(wt).to(DEV), torch.from_numpy(bias).to(DEV),
                              tensor_cores=tc)
         assert tuple(got.shape) == tuple(ref.shape)
@@ -217,11 +217,14 @@ def test_conv3d_mid_matches_float64_torch(cin, cout, kd, d, h, w):
 
 
 @pytest.mark.parametrize("cin,cout,kd,d,h,w", [(32, 32, 3, 4, 10, 12), (64, 64, 3, 3, 7, 67), (64, 64, 1, 1, 9, 33),
-                                               (64, 32, 1, 1, 26, 36), (32, 32, 1, 1, 4, 100), (64, 64, 3, 8, 2, 2)])
-def test_conv3d_mid_tensor_core_kernel_is_fp32_grade(cin, cout, kd, d, h, w):
-    """``mvster_conv3d_mid_tc`` (3xTF32 split, mma.m16n8k8) against float64: the error must stay at the fp32 kernel's
-    level (bound 1e-5 of the output range; measured ~1e-6), far below one TF32 pass (~5e-4) - odd sizes, partial tiles,
-    depth padding, no ReLU, and the cached weight split following an in-place weight update."""
+                                               (64, 32, 1, 1, 26, 36), (32, 32, 1, 1, 4, 100), (64, 64, 3, 8, 2, 2),
+                                               (32, 32, 1, 1, 3, 300), (64, 64, 3, 2, 5, 129)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_conv3d_mid_tensor_core_kernel_is_fp32_grade(cin, cout, kd, d, h, w, mode):
+    """``mvster_conv3d_mid_tc`` (mode 1: mma.m16n8k8) and ``mvster_conv3d_mid_umma`` (mode 2: tcgen05.mma, tensor
+    memory), both with the 3xTF32 operand split, against float64: the error must stay at the fp32 kernel's level (bound
+    1e-5 of the output range; measured 3e-7 .. 4e-6), far below one TF32 pass (~1e-4) - odd sizes, partial tiles, depth
+    padding, no ReLU, and the cached weight split / packing following an in-place weight update."""
     import torch.nn.functional as F
     rng = np.random.RandomState(7 * cin + cout + kd + h)
     x = rng.normal(0, 1, (2, cin, d, h, w)).astype(np.float32)
@@ -234,20 +237,20 @@ def test_conv3d_mid_tensor_core_kernel_is_fp32_grade(cin, cout, kd, d, h, w):
         return r + torch.from_numpy(bias).double().view(1, -1, 1, 1, 1)
 
     n0 = mv.launch_count()
-    got = ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=True)
+    got = ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=mode)
     assert mv.launch_count() - n0 == 2          # the split (once) + the convolution
     ref = ref64(wt)
     scale = max(1.0, ref.abs().max().item())
     err = (got.cpu().double() - ref).abs().max().item()
     assert err < 1e-5 * scale, err
-    simt = ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=False) if h % 2 == 0 and w % 2 == 0 else None
+    simt = ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=0) if h % 2 == 0 and w % 2 == 0 else None
     if simt is not None:
         assert (got - simt).abs().max().item() < 1e-5 * scale
     n0 = mv.launch_count()
-    ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=True)
+    ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=mode)
     assert mv.launch_count() - n0 == 1          # the split is cached ...
     wd.mul_(0.5)                                # ... and follows the weight tensor's version
-    got2 = ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=True)
+    got2 = ops.conv3d_mid(xd, wd, bd, relu=False, tensor_cores=mode)
     assert (got2.cpu().double() - ref64(wt * 0.5)).abs().max().item() < 1e-5 * scale
 
 
