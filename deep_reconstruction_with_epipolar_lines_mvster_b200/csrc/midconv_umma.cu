@@ -94,6 +94,31 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 //   xempty[s] (tcgen05.commit) issuer  -> stagers  every MMA up to chunk k has completed: input stage s and the weight
 //                                                  stage of chunk k are free again
 //   wfull[w]  (bulk-copy bytes)         -> issuer   weight stage w holds its chunk
+// Issued from warp-uniform code: every lane of the issuing warp executes the statement, elect.sync picks the one lane
+// whose predicate lets the instruction through.  (Inside an `if (lane == 0)` region the compiler wraps every UTCHMMA in
+// an ELECT / BRA.U.ANY loop and rebuilds the descriptors with ~20 uniform-datapath instructions per MMA - the single
+// issuing thread then cannot keep the tensor core fed.)
+__device__ __forceinline__ void umma_tf32_elect(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, {%6, %6, %6, %6}, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar)
+        : "memory");
+}
+
 template <int KD, int CIN, int CO>
 __global__ void __launch_bounds__(160) midconv_umma_kernel(const UmmaConvParams p) {
     using K = UmmaCfg<CO>;
@@ -130,53 +155,55 @@ __global__ void __launch_bounds__(160) midconv_umma_kernel(const UmmaConvParams 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 4) {
-        if (lane == 0) {
-            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((128u >> 4) << 24);
-            constexpr int TPU = K::TPU, UPC = K::UPC;
-            const int units = UPC * total;   // weight blocks
-            auto fetch_weights = [&](int u) {   // block u -> ring slot u % kUmWst
-                const uint32_t wf = wfull + 8u * (u % kUmWst);
-                const int c = u / UPC, g = u - UPC * c;
-                const int kd = kd_lo + c / NCH, ch = c % NCH;
-                mbar_expect_tx(wf, (uint32_t)K::WF * 4u);
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(Ws + (u % kUmWst) * K::WF)), "l"(p.wt + (((size_t)kd * NCH + ch) * UPC + g) * K::WF),
-                               "r"((uint32_t)K::WF * 4u), "r"(wf)
-                             : "memory");
-            };
+        // ---- issuer warp: warp-uniform control flow, single-lane side effects ---------------------------------------------
+        constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CO >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr int TPU = K::TPU, UPC = K::UPC;
+        // K-major, no swizzle: LBO (16-byte units, bits 16-29) = distance of the two k-halves, SBO (bits 32-45) = 8 units
+        // between 8-row groups, descriptor version 1 in bits 46-47.  Start addresses are 16-byte aligned and below
+        // 256 KB, so a tap's descriptor is the base's low word plus a constant.
+        constexpr uint32_t DESC_HI = 8u | (1u << 14);
+        constexpr uint32_t A_LBO = (uint32_t)(3 * kUmCols) << 16, B_LBO = (uint32_t)CO << 16;
+        const int units = UPC * total;   // weight blocks
+        auto fetch_weights = [&](int u) {   // block u -> ring slot u % kUmWst (one lane)
+            const uint32_t wf = wfull + 8u * (u % kUmWst);
+            const int c = u / UPC, g = u - UPC * c;
+            const int kd = kd_lo + c / NCH, ch = c % NCH;
+            mbar_expect_tx(wf, (uint32_t)K::WF * 4u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(Ws + (u % kUmWst) * K::WF)), "l"(p.wt + (((size_t)kd * NCH + ch) * UPC + g) * K::WF),
+                           "r"((uint32_t)K::WF * 4u), "r"(wf)
+                         : "memory");
+        };
+        if (lane == 0)
             for (int u = 0; u < kUmWst && u < units; ++u) fetch_weights(u);
+        __syncwarp();
 #pragma unroll 1
-            for (int u = 0; u < units; ++u) {
-                const int k = u / UPC, g = u - UPC * k, s = k & 1, ws = u % kUmWst;
-                if (g == 0) mbar_wait_bounded(xfull + 8u * s, (uint32_t)(k >> 1) & 1u);
-                mbar_wait_bounded(wfull + 8u * ws, (uint32_t)(u / kUmWst) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // with one kernel row per block the row offset is the only run-time part of the A address
-                const uint32_t xa = smem_u32(Xs + s * K::XF) + (UPC == 3 ? (uint32_t)(g * kUmCols * 16) : 0u);
-                const uint32_t wa = smem_u32(Ws + ws * K::WF);
-                const uint32_t acc = tmem + (uint32_t)((k % kUmAcc) * CO);
+        for (int u = 0; u < units; ++u) {
+            const int k = u / UPC, g = u - UPC * k, s = k & 1, ws = u % kUmWst;
+            if (g == 0) mbar_wait_bounded(xfull + 8u * s, (uint32_t)(k >> 1) & 1u);
+            mbar_wait_bounded(wfull + 8u * ws, (uint32_t)(u / kUmWst) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // with one kernel row per block the row offset is the only run-time part of the A address
+            const uint32_t xa = smem_u32(Xs + s * K::XF) + (UPC == 3 ? (uint32_t)(g * kUmCols * 16) : 0u);
+            const uint32_t a_base = (xa >> 4) | A_LBO, b_base = (smem_u32(Ws + ws * K::WF) >> 4) | B_LBO;
+            const uint32_t acc = tmem + (uint32_t)((k % kUmAcc) * CO);
 #pragma unroll
-                for (int tp = 0; tp < TPU; ++tp) {
-                    const int ky = UPC == 3 ? 0 : tp / 3, kx = tp % 3;
-                    const uint32_t a_hi = xa + (uint32_t)((ky * kUmCols + kx) * 16);
-                    const uint32_t a_lo = a_hi + (uint32_t)(K::XF / 2) * 4u;
-                    const uint32_t b_hi = wa + (uint32_t)(tp * 2 * CO * 16);
-                    const uint32_t b_lo = b_hi + (uint32_t)(K::WF / 2) * 4u;
-                    const uint64_t dah = umma_desc(a_hi, 3 * kUmCols, 8), dal = umma_desc(a_lo, 3 * kUmCols, 8);
-                    const uint64_t dbh = umma_desc(b_hi, CO, 8), dbl = umma_desc(b_lo, CO, 8);
-                    umma_tf32(acc, dal, dbh, IDESC, (k >= kUmAcc || g > 0 || tp > 0) ? 1u : 0u);  // small terms first
-                    umma_tf32(acc, dah, dbl, IDESC, 1u);
-                    umma_tf32(acc, dah, dbh, IDESC, 1u);
-                }
-                // commits arrive when every MMA issued so far has completed (they imply tcgen05.fence::before_thread_sync)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(wempty + 8u * ws) : "memory");
-                if (g == UPC - 1)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(xempty + 8u * s) : "memory");
-                // block u-2 has been consumed (the issuer stays two blocks ahead of what it waits for): refill its slot
-                if (u >= 2 && u - 2 + kUmWst < units) {
-                    mbar_wait_bounded(wempty + 8u * ((u - 2) % kUmWst), (uint32_t)((u - 2) / kUmWst) & 1u);
-                    fetch_weights(u - 2 + kUmWst);
-                }
+            for (int tp = 0; tp < TPU; ++tp) {
+                const int ky = UPC == 3 ? 0 : tp / 3, kx = tp % 3;
+                const uint32_t a_hi = a_base + (uint32_t)(ky * kUmCols + kx), a_lo = a_hi + (uint32_t)(K::XF / 2) / 4u;
+                const uint32_t b_hi = b_base + (uint32_t)(tp * 2 * CO), b_lo = b_hi + (uint32_t)(K::WF / 2) / 4u;
+                umma_tf32_elect(acc, a_lo, b_hi, DESC_HI, IDESC, (k >= kUmAcc || g > 0 || tp > 0) ? 1u : 0u);  // small terms first
+                umma_tf32_elect(acc, a_hi, b_lo, DESC_HI, IDESC, 1u);
+                umma_tf32_elect(acc, a_hi, b_hi, DESC_HI, IDESC, 1u);
+            }
+            // commits arrive when every MMA issued so far has completed (they imply tcgen05.fence::before_thread_sync)
+            umma_commit_elect(wempty + 8u * ws);
+            if (g == UPC - 1) umma_commit_elect(xempty + 8u * s);
+            // block u-2 has been consumed (the issuer stays two blocks ahead of what it waits for): refill its slot
+            if (u >= 2 && u - 2 + kUmWst < units) {
+                mbar_wait_bounded(wempty + 8u * ((u - 2) % kUmWst), (uint32_t)((u - 2) / kUmWst) & 1u);
+                if (lane == 0) fetch_weights(u - 2 + kUmWst);
+                __syncwarp();
             }
         }
     } else {

@@ -13,7 +13,9 @@ cols = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("lau
         ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/smem pipe %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
         ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
-        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %")]
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %")]
+cols = [c for c in cols if c[0] in ix]
 out = os.path.join(root, "profiles", "%s_network_kernels_ncu.md" % tag)
 with open(out, "w") as f:
     f.write("# ncu --set full --clock-control none: this library's kernels inside one `MVS4net.forward` (%s)\n\n" % tag)
