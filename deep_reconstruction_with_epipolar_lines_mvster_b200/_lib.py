@@ -25,6 +25,10 @@ _SIGNATURES = {
     "mvster_compose_homography_pair": (c_int, [_P, _P, _P, c_int, _P]),
     "mvster_epi_fwd": (c_int, [_P, POINTER(_P), _P, _P, _P, _P, _P] + [c_int] * 9 + [c_float, c_int, _P]),
     "mvster_epi_fwd_mode": (c_int, [_P, POINTER(_P), _P, _P, _P] + [c_int] * 9 + [c_float, c_int, c_int, c_int, _P]),
+    "mvster_epi_fwd_mode_ex": (c_int, [_P, POINTER(_P), _P, _P, _P, _P] + [c_int] * 9 +
+                               [c_float, c_int, c_int, c_int, _P]),
+    "mvster_epi_bwd_mode": (c_int, [_P, POINTER(_P), _P, _P, _P, _P, _P, _P, POINTER(_P)] + [c_int] * 9 +
+                            [c_float, c_int, c_int, c_int, _P]),
     "mvster_epi_bwd": (c_int, [_P, POINTER(_P), _P, _P, _P, _P, _P, _P, POINTER(_P)] + [c_int] * 9 +
                        [c_float, c_int, _P]),
     "mvster_homo_warp": (c_int, [_P, _P, _P, _P] + [c_int] * 7 + [c_int, _P]),

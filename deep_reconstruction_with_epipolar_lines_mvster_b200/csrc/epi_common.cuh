@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, MVSTER_DIRECT_MINB) epi_fwd_direct_k
             stg_stream(p.out + (((size_t)b * G + sub * GPL + g) * D + d) * plane + pix_off, acc[g][d] * inv);
         if (FUSE_D && p.wsum != nullptr && sub == 0) p.wsum[((size_t)b * D + d) * plane + pix_off] = wsum[d];
     }
+    if (!FUSE_D && p.wsum != nullptr && sub == 0) p.wsum[(size_t)b * plane + pix_off] = wsum[0];  // [B,H,W]
 }
 
 template <int C, int CPG, int D, typename T, bool VAR = false, bool FUSE_D = true>

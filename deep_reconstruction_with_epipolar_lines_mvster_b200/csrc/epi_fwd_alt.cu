@@ -1,4 +1,4 @@
-// K1 forward, the two variants of the reference that no shipped configuration uses (forward only):
+// K1 forward, the two variants of the reference that no shipped configuration uses (backward: epi_bwd_alt.cu):
 //   group_cor=False : per-channel variance cost (ref - warped)^2, G == C   (models/mvs4net_utils.py:1071)
 //   attn_fuse_d=False: one attention weight per pixel and view, max_d softmax_d(score), no temperature, no sqrt(C)
 //                      (models/mvs4net_utils.py:1078-1081,1098)
@@ -35,8 +35,16 @@ using namespace mvster;
 extern "C" int mvster_epi_fwd_mode(const void* ref, const void* const* src, const float* rt, const float* hypo,
                                    float* out, int B, int Nsrc, int C, int G, int D, int H, int W, int Hs, int Ws,
                                    float attn_temp, int dtype, int group_cor, int attn_fuse_d, void* stream) {
+    return mvster_epi_fwd_mode_ex(ref, src, rt, hypo, out, nullptr, B, Nsrc, C, G, D, H, W, Hs, Ws, attn_temp, dtype,
+                                  group_cor, attn_fuse_d, stream);
+}
+
+extern "C" int mvster_epi_fwd_mode_ex(const void* ref, const void* const* src, const float* rt, const float* hypo,
+                                      float* out, float* wsum, int B, int Nsrc, int C, int G, int D, int H, int W,
+                                      int Hs, int Ws, float attn_temp, int dtype, int group_cor, int attn_fuse_d,
+                                      void* stream) {
     if (group_cor && attn_fuse_d)
-        return mvster_epi_fwd(ref, src, rt, hypo, out, nullptr, nullptr, B, Nsrc, C, G, D, H, W, Hs, Ws, attn_temp, dtype,
+        return mvster_epi_fwd(ref, src, rt, hypo, out, wsum, nullptr, B, Nsrc, C, G, D, H, W, Hs, Ws, attn_temp, dtype,
                               stream);
     if (!ref || !src || !rt || !hypo || !out) return fail(MVSTER_ERR_BAD_ARG, "epi_fwd_mode: null pointer");
     if (B <= 0 || Nsrc <= 0 || C <= 0 || G <= 0 || D <= 0 || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0)
@@ -55,7 +63,7 @@ extern "C" int mvster_epi_fwd_mode(const void* ref, const void* const* src, cons
         if (!src[v] || ((uintptr_t)src[v]) % 32) return fail(MVSTER_ERR_ALIGN, "epi_fwd_mode: src[%d] null or misaligned", v);
         p.src[v] = src[v];
     }
-    p.rt = rt; p.hypo = hypo; p.out = out; p.wsum = nullptr; p.weights = nullptr;
+    p.rt = rt; p.hypo = hypo; p.out = out; p.wsum = wsum; p.weights = nullptr;
     p.B = B; p.Nsrc = Nsrc; p.H = H; p.W = W; p.Hs = Hs; p.Ws = Ws;
     p.score_scale = 1.4426950408889634f / attn_temp;
     p.inv_sqrt_c = (float)(1.0 / sqrt((double)C));

@@ -9,6 +9,8 @@
 // pre-composed in float64 on the host (they are the same np.linalg.inv / matmul products the reference forms).
 // cv2.remap(INTER_LINEAR) is emulated bit-for-bit in its coordinate handling: float32 map, fixed point with 5
 // fractional bits (round-half-even), constant-0 border.
+#include <cstddef>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -22,15 +24,16 @@ namespace mvster {
 //   X_ref' = Bk * ([u,v,1] * d_src) + tb        Bk = R_back K_src^-1,      tb = t_back         (back = E_ref E_src^-1)
 //   q'     = G * ([u,v,1] * d_src) + g          G = K_ref Bk,              g = K_ref t_back
 // Only the z row of X_ref' is needed (depth_reprojected).
-struct PairCam {
+struct alignas(16) PairCam {
     double F[9], f[3];
     double G[9], g[3];
     double Bz[3], tbz;
     float Gf[9], gf[3], Bzf[3], tbzf;  // float32 copies of the back-projection for the fast path (see check_pair)
     int src;  // source view index (into the depth stack), < 0 = skip
-    int pad;
+    int pad[3];
 };
-static_assert(sizeof(PairCam) % 8 == 0, "PairCam is copied as doubles");
+static_assert(sizeof(PairCam) % 16 == 0 && offsetof(PairCam, Gf) % 16 == 0,
+              "PairCam is copied as doubles and read with 16-byte shared-memory loads");
 
 __device__ __forceinline__ void mat3_vec(const double* m, double x, double y, double z, double& ox, double& oy,
                                          double& oz) {
@@ -80,6 +83,54 @@ __device__ __forceinline__ double fast_rcp64(double x) {
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
+}
+
+// remap_linear for the fused kernel in two phases, same results.  remap_taps: coordinates -> four tap values and the
+// two fractions, with no conversion instructions (F2I / I2F run on the quarter-rate XU pipe) and NO branches, so that
+// the loads of all the pixels a thread owns are in flight together (the kernel was latency-bound on them).
+//   x * 32 + 1.5 * 2^23 rounds to the nearest-even integer in the mantissa (exact for |x * 32| <= 2^22; the clamp to
+//   +-2^21 sends non-finite and far-away coordinates to a tap index outside any image of <= 32768 px, which is the
+//   constant-0 border); the 5 fractional bits become a float through the 2^23 exponent trick; taps outside the image
+//   are read from the clamped address and replaced by 0.
+// remap_blend: OpenCV's weight products and left-to-right sum.
+struct RemapTaps {
+    float v00, v01, v10, v11, gx, fx, gy, fy;  // tap values, (1 - fx, fx, 1 - fy, fy) with out-of-image taps zeroed
+};
+__device__ __forceinline__ RemapTaps remap_taps(const float* __restrict__ stack, int img_off, int H, int W, float mx,
+                                                float my) {
+    // `stack + img_off` is the image; 32-bit element offsets (the host checks V * H * W < 2^31): one IMAD.WIDE per load
+    constexpr float kMagic = 12582912.0f, kLim = 2097152.0f;  // 1.5 * 2^23, 2^21
+    const float tx = fminf(fmaxf(mx * 32.0f, -kLim), kLim) + kMagic;
+    const float ty = fminf(fmaxf(my * 32.0f, -kLim), kLim) + kMagic;
+    const int ix = __float_as_int(tx) - 0x4B400000, iy = __float_as_int(ty) - 0x4B400000;
+    const int x0 = ix >> 5, y0 = iy >> 5;
+    RemapTaps t;
+    const float fx = (__int_as_float(0x4B000000 | (ix & 31)) - 8388608.0f) * (1.0f / 32.0f);
+    const float fy = (__int_as_float(0x4B000000 | (iy & 31)) - 8388608.0f) * (1.0f / 32.0f);
+    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+    const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+    const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+    const int o0 = img_off + yc0 * W, o1 = img_off + yc1 * W;
+    t.v00 = __ldg(stack + (o0 + xc0));
+    t.v01 = __ldg(stack + (o0 + xc1));
+    t.v10 = __ldg(stack + (o1 + xc0));
+    t.v11 = __ldg(stack + (o1 + xc1));
+    // a tap outside the image counts as 0 (constant border): its weight is zeroed instead of its value (depth maps are
+    // finite, so 0 * v == 0 * 0 up to the sign of zero, which no later operation distinguishes)
+    t.gx = vx0 ? 1.0f - fx : 0.0f;
+    t.fx = vx1 ? fx : 0.0f;
+    t.gy = vy0 ? 1.0f - fy : 0.0f;
+    t.fy = vy1 ? fy : 0.0f;
+    return t;
+}
+__device__ __forceinline__ float remap_blend(const RemapTaps& t) {
+    // no FMA contraction: OpenCV multiplies by a pre-rounded float weight table and adds left to right
+    float acc = __fmul_rn(t.v00, __fmul_rn(t.gx, t.gy));
+    acc = __fadd_rn(acc, __fmul_rn(t.v01, __fmul_rn(t.fx, t.gy)));
+    acc = __fadd_rn(acc, __fmul_rn(t.v10, __fmul_rn(t.gx, t.fy)));
+    acc = __fadd_rn(acc, __fmul_rn(t.v11, __fmul_rn(t.fx, t.fy)));
+    return acc;
 }
 
 // The reference does everything in float64.  Here only what needs it does:
@@ -175,8 +226,45 @@ struct GeoFilterParams {
     int geo_thr;
 };
 
-__global__ void __launch_bounds__(256) geo_filter_kernel(const GeoFilterParams p) {
-    extern __shared__ double cam_s[];  // the S camera blocks of this reference view: read as uniform LDS broadcasts
+// EXACT: the reference's float64 back-projection (:632-667) for the few pixels next to a threshold; out of line so
+// that the hot loop keeps its registers
+struct ExactResult {
+    float depth_rep;
+    int mask;
+};
+__device__ __noinline__ ExactResult exact_back_projection(const PairCam& c, double u, double v, float ds, int x, int y,
+                                                          float d_ref, double pix_thr2, float rel_thr) {
+    const double dsd = (double)ds;
+    const double ux = u * dsd, vx = v * dsd;
+    double px, py, pz;
+    mat3_vec(c.G, ux, vx, dsd, px, py, pz);
+    px += c.g[0]; py += c.g[1]; pz += c.g[2];
+    ExactResult e;
+    e.depth_rep = (float)(c.Bz[0] * ux + c.Bz[1] * vx + c.Bz[2] * dsd + c.tbz);
+    const double ip = 1.0 / pz;
+    const float xr = (float)(px * ip), yr = (float)(py * ip);
+    const double dx = (double)xr - (double)x, dy = (double)yr - (double)y;
+    const double dist2 = dx * dx + dy * dy;
+    const float rel = fabsf(e.depth_rep - d_ref) / d_ref;
+    e.mask = ((dist2 < pix_thr2) && (rel < rel_thr)) ? 1 : 0;
+    return e;
+}
+
+#ifndef MVSTER_FILTER_MINB2
+#define MVSTER_FILTER_MINB2 4
+#endif
+#ifndef MVSTER_FILTER_MINB
+#define MVSTER_FILTER_MINB(PPT) ((PPT) == 4 ? 2 : ((PPT) == 2 ? MVSTER_FILTER_MINB2 : 5))
+#endif
+// Fused filter: a thread owns PPT vertically adjacent reference pixels and walks the S source views.  Per pair the
+// camera block is read once per thread (16-byte shared-memory broadcasts) and serves PPT pixels; the float64 ray
+// A = F [x, y, 1]^T is formed once per pair and stepped down the column with three additions (A is affine in y),
+// so a pixel costs 3 + 4 + 2 float64 operations (q = A d + f, reciprocal, u / v) instead of 9 + 4 + 2, and the PPT
+// independent chains hide each other's latency.  Same decisions as check_pair: float64 up to the remap coordinate,
+// float32 back-projection with the float64 recheck next to the thresholds.
+template <int PPT>
+__global__ void __launch_bounds__(256, MVSTER_FILTER_MINB(PPT)) geo_filter_kernel(const GeoFilterParams p) {
+    extern __shared__ __align__(16) double cam_s[];  // the S camera blocks of this reference view (uniform LDS broadcasts)
     const int r = blockIdx.z;
     {
         const double* src = reinterpret_cast<const double*>(p.cams + (size_t)r * p.S);
@@ -185,32 +273,94 @@ __global__ void __launch_bounds__(256) geo_filter_kernel(const GeoFilterParams p
     }
     __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= p.W || y >= p.H) return;
-    const size_t plane = (size_t)p.H * p.W;
-    const size_t i = (size_t)y * p.W + x;
+    const int yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * PPT;
+    if (x >= p.W || yb >= p.H) return;
+    const int H = p.H, W = p.W;
+    const size_t plane = (size_t)H * W;
     const int ref = p.refs[r];
-    const float d_ref = p.depths[(size_t)ref * plane + i];
-    int votes = 0;
-    float sum = 0.0f;  // float32 running sum, like sum(list of float32 arrays) at :744
+    const float* dref_p = p.depths + (size_t)ref * plane;
+    float d_ref[PPT], inv_d[PPT], sum[PPT], yf[PPT];
+    double dr[PPT];
+    int votes[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int y = min(yb + k, H - 1);  // rows past the image repeat the last one and are not stored
+        d_ref[k] = dref_p[(size_t)y * W + x];
+        dr[k] = (double)d_ref[k];
+        inv_d[k] = 1.0f / d_ref[k];
+        yf[k] = (float)(yb + k);
+        sum[k] = 0.0f;  // float32 running sum, like sum(list of float32 arrays) at :744
+        votes[k] = 0;
+    }
+    const double xd = (double)x, yd = (double)yb;
+    const float xf = (float)x;
+    const float thr2 = (float)p.pix_thr2, rel_thr = p.rel_thr;
+    const float thr2_band = 0.008f * thr2, rel_band = 3e-4f * rel_thr;
     const PairCam* cams = reinterpret_cast<const PairCam*>(cam_s);
+#pragma unroll 1
     for (int s = 0; s < p.S; ++s) {
         const PairCam& c = cams[s];
         if (c.src < 0) continue;
-        const PairResult pr = check_pair(c, p.depths + (size_t)c.src * plane, p.H, p.W, x, y, d_ref, p.pix_thr2,
-                                         p.rel_thr);
-        votes += pr.mask ? 1 : 0;
-        sum = __fadd_rn(sum, pr.mask ? pr.depth_reprojected : 0.0f);
+        const double2* Fd = reinterpret_cast<const double2*>(c.F);      // F[0..8], f[0..2]: 12 contiguous doubles
+        const double2 F01 = Fd[0], F23 = Fd[1], F45 = Fd[2], F67 = Fd[3], F8f0 = Fd[4], f12 = Fd[5];
+        const float4* Gq = reinterpret_cast<const float4*>(c.Gf);       // Gf[0..8], gf[0..2], Bzf[0..2], tbzf
+        const float4 G0 = Gq[0], G1 = Gq[1], G2 = Gq[2], G3 = Gq[3];
+        const int src_off = c.src * (H * W);
+        double ax = fma(F01.x, xd, fma(F01.y, yd, F23.x));
+        double ay = fma(F23.y, xd, fma(F45.x, yd, F45.y));
+        double az = fma(F67.x, xd, fma(F67.y, yd, F8f0.x));
+        // phase 1, all pixels of the thread: reference pixel -> 3-D -> source pixel (:619-631) in float64, tap loads
+        double u[PPT], v[PPT];
+        RemapTaps taps[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            if (k > 0) { ax += F01.y; ay += F45.x; az += F67.y; }
+            const double qx = fma(ax, dr[k], F8f0.y), qy = fma(ay, dr[k], f12.x), qz = fma(az, dr[k], f12.y);
+            const double iq = fast_rcp64(qz);
+            u[k] = qx * iq;
+            v[k] = qy * iq;
+            taps[k] = remap_taps(p.depths, src_off, H, W, (float)u[k], (float)v[k]);
+        }
+        // phase 2: source pixel -> 3-D -> reference pixel (:632-647) in float32, thresholds, float64 recheck
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const float xs = (float)u[k], ys = (float)v[k];
+            const float ds = remap_blend(taps[k]);
+            const float ux = xs * ds, vx = ys * ds;
+            const float px = fmaf(G0.x, ux, fmaf(G0.y, vx, fmaf(G0.z, ds, G2.y)));
+            const float py = fmaf(G0.w, ux, fmaf(G1.x, vx, fmaf(G1.y, ds, G2.z)));
+            const float pz = fmaf(G1.z, ux, fmaf(G1.w, vx, fmaf(G2.x, ds, G2.w)));
+            float dep = fmaf(G3.x, ux, fmaf(G3.y, vx, fmaf(G3.z, ds, G3.w)));
+            const float ip = fast_rcp(pz);
+            const float dx = fmaf(px, ip, -xf), dy = fmaf(py, ip, -yf[k]);
+            const float dist2 = fmaf(dx, dx, dy * dy);
+            const float rel = fabsf(dep - d_ref[k]) * inv_d[k];
+            bool m = (dist2 < thr2) && (rel < rel_thr);
+            if ((fabsf(dist2 - thr2) < thr2_band) || (fabsf(rel - rel_thr) < rel_band)) {
+                const ExactResult e = exact_back_projection(c, u[k], v[k], ds, x, yb + k, d_ref[k], p.pix_thr2, rel_thr);
+                m = e.mask != 0;
+                dep = e.depth_rep;
+            }
+            votes[k] += m ? 1 : 0;
+            sum[k] = __fadd_rn(sum[k], m ? dep : 0.0f);
+        }
     }
-    const size_t o = (size_t)r * plane + i;
-    const bool ph = p.confs[(size_t)ref * plane + i] > p.photo_thr;  // :716
-    const bool ge = votes >= p.geo_thr;                               // :746
-    p.photo[o] = ph;
-    p.geo[o] = ge;
-    p.final_mask[o] = ph && ge;                                       // :749
-    // :744 - float32 sum divided by an int32 count gives float64 in NumPy; rounded to float32 on output
-    p.depth_avg[o] = (float)((double)__fadd_rn(sum, d_ref) / (double)(votes + 1));
-    if (p.geo_sum != nullptr) p.geo_sum[o] = votes;
+    const float* conf_p = p.confs + (size_t)ref * plane;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int y = yb + k;
+        if (y >= H) break;
+        const size_t i = (size_t)y * W + x;
+        const size_t o = (size_t)r * plane + i;
+        const bool ph = conf_p[i] > p.photo_thr;   // :716
+        const bool ge = votes[k] >= p.geo_thr;     // :746
+        p.photo[o] = ph;
+        p.geo[o] = ge;
+        p.final_mask[o] = ph && ge;                // :749
+        // :744 - float32 sum divided by an int32 count gives float64 in NumPy; rounded to float32 on output
+        p.depth_avg[o] = (float)((double)__fadd_rn(sum[k], d_ref[k]) / (double)(votes[k] + 1));
+        if (p.geo_sum != nullptr) p.geo_sum[o] = votes[k];
+    }
 }
 
 // ---- host: float64 camera algebra (the same products np.linalg.inv / np.matmul form in the reference) -------
@@ -285,7 +435,7 @@ static void make_pair_cam(const double* Kr, const double* Er, const double* Ks, 
     for (int i = 0; i < 3; ++i) { c->gf[i] = (float)c->g[i]; c->Bzf[i] = (float)c->Bz[i]; }
     c->tbzf = (float)c->tbz;
     c->src = src;
-    c->pad = 0;
+    c->pad[0] = c->pad[1] = c->pad[2] = 0;
 }
 
 // The camera blocks are staged through the stream-ordered allocator.  Its default pool gives memory back to the
@@ -341,6 +491,8 @@ extern "C" int mvster_geo_filter(const float* depths, const float* confs, const 
         return fail(MVSTER_ERR_BAD_ARG, "geo_filter: null pointer");
     if (V <= 0 || R <= 0 || S < 0 || H <= 0 || W <= 0) return fail(MVSTER_ERR_BAD_ARG, "geo_filter: bad dimension");
     if (R > 65535) return fail(MVSTER_ERR_UNSUPPORTED, "geo_filter: more than 65535 reference views per call");
+    if (H > 32768 || W > 32768 || (double)V * H * W >= 2147483648.0)
+        return fail(MVSTER_ERR_UNSUPPORTED, "geo_filter: depth maps larger than 32768 px per side or a stack of 2^31 px");
     DeviceGuard guard(depth_avg);
     if (guard.status != MVSTER_OK) return guard.status;
     cudaStream_t s = (cudaStream_t)stream;
@@ -370,10 +522,14 @@ extern "C" int mvster_geo_filter(const float* depths, const float* confs, const 
     GeoFilterParams p{depths, confs, reinterpret_cast<const PairCam*>(dev), reinterpret_cast<const int*>(dev + cam_bytes),
                       photo, geo, final_mask, depth_avg, geo_sum, Sa, H, W, condmask_pixel * condmask_pixel, (float)condmask_depth,
                       (float)photomask, geomask};
-    dim3 grid((W + 31) / 32, (H + 7) / 8, R);
+    // reference pixels per thread (a column of PPT rows; CTA tile 32 x 8*PPT); MVSTER_FILTER_PPT=1|2 for A/B timing (default 4)
+    static const int ppt = [] { const char* e = getenv("MVSTER_FILTER_PPT"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
+    dim3 grid((W + 31) / 32, (H + 8 * ppt - 1) / (8 * ppt), R);
     const size_t cam_smem = (size_t)Sa * sizeof(PairCam);
     if (cam_smem > 48 * 1024) { cudaFreeAsync(dev, s); return fail(MVSTER_ERR_UNSUPPORTED, "geo_filter: more than %d source views per reference view", (int)(48 * 1024 / sizeof(PairCam))); }
-    geo_filter_kernel<<<grid, 256, cam_smem, s>>>(p);
+    if (ppt == 1) geo_filter_kernel<1><<<grid, 256, cam_smem, s>>>(p);
+    else if (ppt == 2) geo_filter_kernel<2><<<grid, 256, cam_smem, s>>>(p);
+    else geo_filter_kernel<4><<<grid, 256, cam_smem, s>>>(p);
     count_launch();
     cudaError_t le = cudaGetLastError();
     cudaFreeAsync(dev, s);

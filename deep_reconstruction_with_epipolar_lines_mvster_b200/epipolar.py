@@ -60,19 +60,46 @@ def epipolar_aggregate(features: Sequence[torch.Tensor], proj_matrices: torch.Te
                                    feature_dtype, *features[1:])
 
 
+class EpipolarAggregateVariant(torch.autograd.Function):
+    """``EpipolarAggregate`` for the reference's ``group_cor=False`` (variance cost, mvs4net_utils.py:1071) and / or
+    ``attn_fuse_d=False`` (per-pixel weight, :1078-1081,1098) options: ``mvster_epi_fwd_mode_ex`` forward,
+    ``mvster_epi_bwd_mode`` backward, fp32 features.  Saves the inputs, the volume and the weight sums only."""
+
+    @staticmethod
+    def forward(ctx, ref, hypo, proj, groups, attn_temp, group_cor, attn_fuse_d, *srcs):
+        ref_n = ops.to_nhwc(ref, torch.float32)
+        srcs_n = [ops.to_nhwc(s, torch.float32) for s in srcs]
+        rt = ops.compose_homographies(proj)
+        needs_grad = any(ctx.needs_input_grad[i] for i in [0] + list(range(7, 7 + len(srcs))))
+        res = ops.epi_fwd_mode(ref_n, srcs_n, rt, hypo, groups, attn_temp, group_cor, attn_fuse_d, want_wsum=needs_grad)
+        if not needs_grad:
+            return res
+        out, wsum = res
+        ctx.save_for_backward(ref_n, rt, hypo.detach().float().contiguous(), out, wsum, *srcs_n)
+        ctx.cfg = (groups, attn_temp, group_cor, attn_fuse_d)
+        ctx.in_dtypes = [ref.dtype] + [s.dtype for s in srcs]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        ref_n, rt, hypo, out, wsum, *srcs_n = ctx.saved_tensors
+        groups, attn_temp, group_cor, attn_fuse_d = ctx.cfg
+        grad_ref, grad_srcs = ops.epi_bwd_mode(ref_n, srcs_n, rt, hypo, out, wsum, gout, groups, attn_temp, group_cor,
+                                               attn_fuse_d)
+        gr = grad_ref.permute(0, 3, 1, 2).to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
+        gs = [g.permute(0, 3, 1, 2).to(dt) if ctx.needs_input_grad[7 + i] else None
+              for i, (g, dt) in enumerate(zip(grad_srcs, ctx.in_dtypes[1:]))]
+        return (gr, None, None, None, None, None, None, *gs)
+
+
 def epipolar_aggregate_variant(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, depth_hypo: torch.Tensor,
                                group_cor: bool, group_cor_dim: int, attn_fuse_d: bool, attn_temp: float) -> torch.Tensor:
     """The reference's ``group_cor=False`` (variance cost, mvs4net_utils.py:1071) and/or ``attn_fuse_d=False``
-    (per-pixel weight, :1078-1081) options.  Forward only: no shipped configuration trains with them."""
-    if any(f.requires_grad for f in features) and torch.is_grad_enabled():
-        raise NotImplementedError("stagenet(B200): group_cor=False / attn_fuse_d=False have a fused forward kernel only; "
-                                  "run them under torch.no_grad() (every shipped training config uses the defaults)")
-    with torch.no_grad():
-        ref_n = ops.to_nhwc(features[0], torch.float32)
-        srcs_n = [ops.to_nhwc(s, torch.float32) for s in features[1:]]
-        rt = ops.compose_homographies(proj_matrices)
-        return ops.epi_fwd_mode(ref_n, srcs_n, rt, depth_hypo, int(group_cor_dim), float(attn_temp), bool(group_cor),
-                                bool(attn_fuse_d))
+    (per-pixel weight, :1078-1081) options, differentiable with respect to the features like the default path."""
+    if len(features) < 2:
+        raise RuntimeError("epipolar_aggregate_variant needs at least one source view")
+    return EpipolarAggregateVariant.apply(features[0], depth_hypo, proj_matrices, int(group_cor_dim), float(attn_temp),
+                                          bool(group_cor), bool(attn_fuse_d), *features[1:])
 
 
 def epipolar_weights(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, depth_hypo: torch.Tensor,

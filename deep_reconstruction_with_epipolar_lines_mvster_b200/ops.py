@@ -146,18 +146,47 @@ def epi_fwd(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch
 
 
 def epi_fwd_mode(ref_nhwc: torch.Tensor, srcs_nhwc: Sequence[torch.Tensor], rt: torch.Tensor, hypo: torch.Tensor,
-                 groups: int, attn_temp: float, group_cor: bool, attn_fuse_d: bool) -> torch.Tensor:
-    """Forward of the reference's non-default options (variance cost / per-pixel weight); inference only."""
+                 groups: int, attn_temp: float, group_cor: bool, attn_fuse_d: bool, want_wsum: bool = False):
+    """Forward of the reference's non-default options (variance cost / per-pixel weight).  Returns the volume, or
+    ``(volume, wsum)`` with ``want_wsum`` (what ``epi_bwd_mode`` needs: ``[B,D,H,W]``, or ``[B,H,W]`` when
+    ``attn_fuse_d`` is off)."""
     hypo, d = _check_k1_inputs(ref_nhwc, srcs_nhwc, rt, hypo)
     b, h, w, c = ref_nhwc.shape
     nsrc = len(srcs_nhwc)
     hs, ws = srcs_nhwc[0].shape[1:3]
     g = groups if group_cor else c
     out = torch.empty((b, g, d, h, w), device=ref_nhwc.device, dtype=torch.float32)
-    _lib.check(_lib.load().mvster_epi_fwd_mode(
-        _ptr(ref_nhwc), _ptr_array(srcs_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), b, nsrc, c, g, d, h, w, hs, ws,
-        float(attn_temp), _dtype_code(ref_nhwc), int(bool(group_cor)), int(bool(attn_fuse_d)), _stream(ref_nhwc)))
-    return out
+    wsum = None
+    if want_wsum:
+        wsum = torch.empty((b, d, h, w) if attn_fuse_d else (b, h, w), device=ref_nhwc.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_epi_fwd_mode_ex(
+        _ptr(ref_nhwc), _ptr_array(srcs_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), _ptr(wsum) if want_wsum else None,
+        b, nsrc, c, g, d, h, w, hs, ws, float(attn_temp), _dtype_code(ref_nhwc), int(bool(group_cor)),
+        int(bool(attn_fuse_d)), _stream(ref_nhwc)))
+    return (out, wsum) if want_wsum else out
+
+
+def epi_bwd_mode(ref_nhwc, srcs_nhwc, rt, hypo, out, wsum, gout, groups: int, attn_temp: float, group_cor: bool,
+                 attn_fuse_d: bool) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """K1 backward of the non-default options.  Returns ``(grad_ref [B,H,W,C], [grad_src_v [B,Hs,Ws,C]])`` fp32."""
+    hypo, d = _check_k1_inputs(ref_nhwc, srcs_nhwc, rt, hypo)
+    b, h, w, c = ref_nhwc.shape
+    nsrc = len(srcs_nhwc)
+    hs, ws = srcs_nhwc[0].shape[1:3]
+    g = groups if group_cor else c
+    gout = _f32c(gout, "grad_output")
+    want_ws = (b, d, h, w) if attn_fuse_d else (b, h, w)
+    if tuple(gout.shape) != (b, g, d, h, w) or tuple(out.shape) != (b, g, d, h, w) or tuple(wsum.shape) != want_ws:
+        raise RuntimeError("grad_output / out must be [B,G,D,H,W] and wsum %s of the forward call" % (want_ws,))
+    dev = ref_nhwc.device
+    grad_ref = torch.empty((b, h, w, c), device=dev, dtype=torch.float32)
+    grad_all = torch.zeros((nsrc, b, hs, ws, c), device=dev, dtype=torch.float32)
+    grad_srcs = [grad_all[v] for v in range(nsrc)]
+    _lib.check(_lib.load().mvster_epi_bwd_mode(
+        _ptr(ref_nhwc), _ptr_array(srcs_nhwc), _ptr(rt), _ptr(hypo), _ptr(out), _ptr(wsum), _ptr(gout),
+        _ptr(grad_ref), _ptr_array(grad_srcs), b, nsrc, c, g, d, h, w, hs, ws, float(attn_temp),
+        _dtype_code(ref_nhwc), int(bool(group_cor)), int(bool(attn_fuse_d)), _stream(ref_nhwc)))
+    return grad_ref, grad_srcs
 
 
 def epi_bwd(ref_nhwc, srcs_nhwc, rt, hypo, out, wsum, gout, groups: int, attn_temp: float

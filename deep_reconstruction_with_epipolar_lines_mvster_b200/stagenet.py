@@ -74,7 +74,7 @@ class stagenet(nn.Module):
         if group_cor and self.attn_fuse_d:
             cor_feats = EpipolarAggregate.apply(ref_feature, depth_hypo, proj_matrices, int(group_cor_dim),
                                                 float(self.attn_temp), self.feature_dtype, *features[1:])
-        else:  # variance cost (:1071) and / or per-pixel weight (:1078-1081): fused forward kernel, inference only
+        else:  # variance cost (:1071) and / or per-pixel weight (:1078-1081): fused forward + backward kernels, fp32
             cor_feats = epipolar_aggregate_variant(features, proj_matrices, depth_hypo, bool(group_cor), int(group_cor_dim),
                                                    bool(self.attn_fuse_d), float(self.attn_temp))
         # step 3: regularisation (unchanged, cuDNN)

@@ -80,7 +80,7 @@ int mvster_epi_fwd(const void* ref, const void* const* src, const float* rt, con
                    float* wsum, float* weights, int B, int Nsrc, int C, int G, int D, int H, int W, int Hs, int Ws,
                    float attn_temp, int dtype, void* stream);
 
-/* Same forward with the two reference options that no shipped configuration uses, forward only (inference):
+/* Same forward with the two reference options that no shipped configuration uses:
  *   group_cor = 0   : per-channel variance cost (ref - warped)^2, G must equal C  (models/mvs4net_utils.py:1071)
  *   attn_fuse_d = 0 : one weight per pixel and view, max_D softmax_D(score), no temperature, no sqrt(C)
  *                     (models/mvs4net_utils.py:1078-1081,1098)
@@ -88,6 +88,11 @@ int mvster_epi_fwd(const void* ref, const void* const* src, const float* rt, con
 int mvster_epi_fwd_mode(const void* ref, const void* const* src, const float* rt, const float* hypo, float* out, int B,
                         int Nsrc, int C, int G, int D, int H, int W, int Hs, int Ws, float attn_temp, int dtype,
                         int group_cor, int attn_fuse_d, void* stream);
+/* mvster_epi_fwd_mode that also stores what mvster_epi_bwd_mode needs: wsum (NULL ok) is [B, D, H, W] when
+ * attn_fuse_d = 1 and [B, H, W] when attn_fuse_d = 0 (cor_weight_sum is per pixel there, :1080). */
+int mvster_epi_fwd_mode_ex(const void* ref, const void* const* src, const float* rt, const float* hypo, float* out,
+                           float* wsum, int B, int Nsrc, int C, int G, int D, int H, int W, int Hs, int Ws,
+                           float attn_temp, int dtype, int group_cor, int attn_fuse_d, void* stream);
 
 /* ---- K1 backward -----------------------------------------------------------------------------------------
  * Replaces autograd through the same lines (grid_sampler_2d_backward, softmax_backward, ...).  Gradients flow to
@@ -102,6 +107,15 @@ int mvster_epi_fwd_mode(const void* ref, const void* const* src, const float* rt
 int mvster_epi_bwd(const void* ref, const void* const* src, const float* rt, const float* hypo, const float* out,
                    const float* wsum, const float* gout, float* grad_ref, float* const* grad_src, int B, int Nsrc,
                    int C, int G, int D, int H, int W, int Hs, int Ws, float attn_temp, int dtype, void* stream);
+
+/* Backward of mvster_epi_fwd_mode_ex: autograd of models/mvs4net_utils.py:1066-1100 with group_cor=False (gradient
+ * of (ref - warped)^2, :1071) and / or attn_fuse_d=False (gradient through max_D softmax_D, :1079, which reaches the
+ * first maximum only, as torch.max(dim) does).  Arguments as mvster_epi_bwd; wsum as written by mvster_epi_fwd_mode_ex;
+ * fp32 features only; group_cor = attn_fuse_d = 1 forwards to mvster_epi_bwd. */
+int mvster_epi_bwd_mode(const void* ref, const void* const* src, const float* rt, const float* hypo, const float* out,
+                        const float* wsum, const float* gout, float* grad_ref, float* const* grad_src, int B, int Nsrc,
+                        int C, int G, int D, int H, int W, int Hs, int Ws, float attn_temp, int dtype, int group_cor,
+                        int attn_fuse_d, void* stream);
 
 /* ---- homo_warping compatibility (models/mvs4net_utils.py:21-67): materialises [B, C, D, H, W] fp32 -------- */
 int mvster_homo_warp(const void* src, const float* rt /* dev [B,12] */, const float* hypo, float* warped, int B,

@@ -15,6 +15,7 @@
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -164,7 +165,10 @@ def bench_filter(args, dev):
     by = 441 * h * w * 4 + 49 * (2 * h * w * 4 + h * w * 4 + 3 * h * w)
     line = {"bench": "filter_49x9_512x640", "ms_per_scene": ms, "scenes_per_s": 1e3 / ms, "pair_checks_per_s": 441e3 / ms,
             "algorithmic_GB": by / 1e9, "GBps": by / ms / 1e6, "geo_mask_mean": float(geo.float().mean()),
-            "final_mask_mean": float(final.float().mean())}
+            "final_mask_mean": float(final.float().mean()),
+            "sha1_masks": hashlib.sha1(torch.stack([photo, geo, final]).cpu().numpy().tobytes()).hexdigest()[:16],
+            "sha1_depth_avg": hashlib.sha1(avg.cpu().numpy().tobytes()).hexdigest()[:16],
+            "ppt": os.environ.get("MVSTER_FILTER_PPT", "4")}
     if args.cpu_filter_pairs > 0:
         from oracle import mvster_oracle as O
         t0 = time.perf_counter()

@@ -127,9 +127,11 @@ def test_k1_rejects_unsupported_configs(golden):
     g = golden("k1_stage4")
     feats = _features(g)
     proj, hypo = _cuda(g["proj"]), _cuda(g["hypo"])
-    # the variants have a forward kernel only: asking for gradients must fail loudly
-    with pytest.raises(NotImplementedError):
-        mv.epipolar_aggregate_variant([f.clone().requires_grad_(True) for f in feats], proj, hypo, False, 8, True, 2.0)
+    # the variance cost has one output channel per feature channel: group_cor=False with G != C is an error
+    with pytest.raises(RuntimeError, match="G == C|must be"):
+        ops.epi_bwd_mode(ops.to_nhwc(feats[0], torch.float32), [ops.to_nhwc(f, torch.float32) for f in feats[1:]],
+                         ops.compose_homographies(proj), hypo, torch.zeros(1, 4, 4, 24, 33, device=DEV),
+                         torch.ones(1, 4, 24, 33, device=DEV), torch.zeros(1, 4, 4, 24, 33, device=DEV), 4, 2.0, False, True)
     with pytest.raises(RuntimeError, match="not in"):
         bad = [torch.zeros(1, 24, 8, 8, device=DEV) for _ in range(2)]
         mv.epipolar_aggregate(bad, proj[:, :2], torch.ones(1, 4, 8, 8, device=DEV), 4, 2.0)
@@ -427,6 +429,37 @@ def test_k1_reference_option_variants(golden, name, group_cor, attn_fuse_d):
     with torch.no_grad():
         net(feats, proj, hypo, regnet, 1, group_cor=group_cor, group_cor_dim=groups, split_itv=1.0)
     assert torch.equal(seen["x"], got)
+
+
+@pytest.mark.parametrize("group_cor,attn_fuse_d", [(False, True), (True, False), (False, False)])
+@pytest.mark.parametrize("name", ["k1_stage2", "k1_stage4", "k1_oob"])
+def test_k1_option_variants_backward_matches_reference_autograd(golden, name, group_cor, attn_fuse_d):
+    """Volume and feature gradients of group_cor=False / attn_fuse_d=False against the reference's own autograd
+    (tests/golden/k1_modes.npz from make_golden_modes.py), through the functional form and the drop-in stagenet."""
+    g, m = golden(name), golden("k1_modes")
+    key = "%s/%d%d/" % (name, int(group_cor), int(attn_fuse_d))
+    groups, temp = int(g["groups"]), float(g["attn_temp"])
+    proj, hypo, gout = _cuda(g["proj"]), _cuda(g["hypo"]), _cuda(m[key + "gout"])
+    for through_stagenet in (False, True):
+        feats = _features(g, requires_grad=True)
+        if through_stagenet:
+            seen = {}
+
+            def regnet(x):
+                seen["x"] = x
+                return x.sum(1)
+
+            net = mv.stagenet(inverse_depth=True, attn_fuse_d=attn_fuse_d, attn_temp=temp).eval()
+            net(feats, proj, hypo, regnet, 1, group_cor=group_cor, group_cor_dim=groups, split_itv=1.0)
+            vol = seen["x"]
+        else:
+            vol = mv.epipolar_aggregate_variant(feats, proj, hypo, group_cor, groups, attn_fuse_d, temp)
+        assert np.abs(vol.detach().cpu().numpy() - m[key + "volume"]).max() < 1e-4
+        (vol * gout).sum().backward()
+        want = [m[key + "grad_ref"]] + [m[key + "grad_srcs"][:, v] for v in range(g["srcs"].shape[1])]
+        for i, (f, wg) in enumerate(zip(feats, want)):
+            scale = max(1.0, np.abs(wg).max())
+            assert np.abs(f.grad.cpu().numpy() - wg).max() < 2e-4 * scale, (key, i, through_stagenet)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process (nn.DataParallel pattern)")
