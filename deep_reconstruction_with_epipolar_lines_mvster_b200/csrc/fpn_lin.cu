@@ -1,0 +1,224 @@
+// FPN4 top-down step in its linearised form, the finest level's replacement for
+// fpn_topdown_kernel.
+//
+// Reference (models/mvs4net_utils.py:488-495):   intra = up2(prev) + inner(lat);   out = out_conv(intra)
+// with up2 = bilinear x2 (align_corners=True), inner = 1x1 convolution with bias (CL -> 64), out_conv = 3x3 convolution
+// without bias (64 -> CO), zero padding.  Every step is linear, so the 64-channel full-resolution `intra` need not
+// exist, not even in shared memory:
+//     out[x] = sum_tap W[tap] intra[x + tap]                                            (taps inside the image only)
+//            = sum_tap bilinear(P_tap)(x + tap)  +  sum_tap (W[tap] Wi) lat[x + tap]  +  sum_tap W[tap] bi
+//     P_tap  = W[tap] prev          9 x CO channels at HALF resolution: one [pixels x 64] x [64 x 9 CO] GEMM (cuBLAS, by
+//                                   the caller - a plain library GEMM) instead of a 64 -> CO 3x3 convolution at full
+//                                   resolution: 64 x 9 CO FMAs per coarse pixel = a quarter of the work per fine pixel
+//     W[tap] Wi                     a CL -> CO 3x3 convolution on the encoder map (composed in float64 on the host)
+// Per fine pixel: 9 x 4 x CO (bilinear taps of P) + 9 x CL x CO (lateral) FMAs = 864 for CL = CO = 8 instead of
+// 64 x 9 x CO + 64 x (CL + 4) = 5376.  The result differs from the reference's evaluation order by fp32 rounding
+// only (parity bound of the FPN tests: 3e-5 of the output range against float64).
+//
+// A CTA owns a 32 x 8 output tile: the P rows its (tile + halo) pixels interpolate from (<= 7 x 20 coarse pixels x
+// 9 CO channels, NHWC, copied with 16-byte loads into a padded shared-memory tile so that the lanes of a quarter-warp
+// hit distinct bank groups) and the lateral tile (+1 halo, zero outside the image); a thread owns one pixel and all
+// CO channels; the composed lateral weights and the bias terms travel as kernel parameters (uniform constant operands).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mvster {
+
+constexpr int kLinTW = 32, kLinTH = 8;      // output tile
+constexpr int kLinRC = 20, kLinRR = 7;      // coarse region held per CTA (columns, rows)
+constexpr int kLinLW = 36, kLinLH = kLinTH + 2;  // lateral tile row stride / rows (tile + halo)
+constexpr int kLinThreads = kLinTW * kLinTH;
+
+template <int CL, int CO>
+struct LinParams {
+    float wc[9 * CL * CO];  // [tap][ci][co]  composed W[tap] Wi
+    float bc[9 * CO];       // [tap][co]      W[tap] bi
+    const float* P;         // [B, H/2, W/2, 9*CO] NHWC: P[.., tap*CO + co] = sum_c W[co,c,tap] prev[c]
+    const float* lat;       // [B, CL, H, W] planar
+    void* feat;             // [B, H, W, CO] NHWC, fp32 or bf16
+    int B, H, W;
+    float sy, sx;           // align_corners=True source scale (Hl-1)/(H-1), (Wl-1)/(W-1)
+};
+
+template <int CL, int CO>
+struct LinGeom {
+    static constexpr int PS = 9 * CO + 4;  // floats per coarse pixel; PS * 4 B = 16 B * odd: columns shift bank groups
+    static constexpr int SMEM = (kLinRR * kLinRC * PS + CL * kLinLH * kLinLW) * 4;
+};
+
+__device__ __forceinline__ unsigned lin_pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned*>(&v);
+}
+
+template <int CL, int CO, typename OutT>
+__global__ void __launch_bounds__(kLinThreads, (CO == 8) ? 3 : 2) fpn_lin_kernel(const __grid_constant__ LinParams<CL, CO> p) {
+    constexpr int PS = LinGeom<CL, CO>::PS, PC = 9 * CO, Q = PC / 4;
+    extern __shared__ __align__(16) float lin_smem[];
+    float* Ps = lin_smem;                         // [kLinRR][kLinRC][PS]
+    float* Ls = lin_smem + kLinRR * kLinRC * PS;  // [CL][kLinLH][kLinLW]
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int tx0 = blockIdx.x * kLinTW, ty0 = blockIdx.y * kLinTH;
+    const int H = p.H, W = p.W, Hl = H / 2, Wl = W / 2;
+
+    // coarse region that the tile + halo interpolates from (source = scale * dst is monotone in dst)
+    const int lx0 = (int)(p.sx * (float)max(tx0 - 1, 0));
+    const int lx1 = min((int)(p.sx * (float)min(tx0 + kLinTW, W - 1)) + 1, Wl - 1);
+    const int ly0 = (int)(p.sy * (float)max(ty0 - 1, 0));
+    const int ly1 = min((int)(p.sy * (float)min(ty0 + kLinTH, H - 1)) + 1, Hl - 1);
+    const int nc = min(lx1 - lx0 + 1, kLinRC), nr = min(ly1 - ly0 + 1, kLinRR);
+    {
+        const int per_row = nc * Q;
+        for (int i = tid; i < nr * per_row; i += kLinThreads) {
+            const int r = i / per_row, rem = i - r * per_row;
+            const int c = rem / Q, j = rem - c * Q;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(
+                p.P + (((size_t)b * Hl + ly0 + r) * Wl + lx0) * PC) + rem);
+            *reinterpret_cast<float4*>(Ps + (r * kLinRC + c) * PS + 4 * j) = v;
+        }
+        constexpr int LHW = kLinLH * (kLinTW + 2);
+        for (int i = tid; i < CL * LHW; i += kLinThreads) {
+            const int ci = i / LHW, rem = i - ci * LHW;
+            const int ry = rem / (kLinTW + 2), rx = rem - ry * (kLinTW + 2);
+            const int gy = ty0 - 1 + ry, gx = tx0 - 1 + rx;
+            const bool inside = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+            Ls[(ci * kLinLH + ry) * kLinLW + rx] =
+                inside ? __ldg(p.lat + (((size_t)b * CL + ci) * H + gy) * W + gx) : 0.0f;
+        }
+    }
+    __syncthreads();
+
+    const int px = tid & 31, py = tid >> 5;
+    const int x = tx0 + px, y = ty0 + py;
+    if (x >= W || y >= H) return;
+
+    // the three source columns of the taps (dx = -1, 0, 1): coarse column pair and weights, ATen's arithmetic
+    int cx0[3], cx1[3];
+    float wx0[3], wx1[3];
+    bool vx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int qx = x + k - 1;
+        vx[k] = (unsigned)qx < (unsigned)W;
+        const float fx = p.sx * (float)max(qx, 0);
+        const int x0 = (int)fx;
+        cx0[k] = min(x0 - lx0, kLinRC - 1);
+        cx1[k] = min(x0 + (x0 < Wl - 1) - lx0, kLinRC - 1);
+        wx1[k] = fx - (float)x0;
+        wx0[k] = 1.0f - wx1[k];
+    }
+    float acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = 0.0f;
+
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int qy = y + ky - 1;
+        if ((unsigned)qy >= (unsigned)H) continue;  // warp-uniform: a warp is one image row
+        const float fy = p.sy * (float)qy;
+        const int y0 = (int)fy;
+        const int r0 = min(y0 - ly0, kLinRR - 1), r1 = min(y0 + (y0 < Hl - 1) - ly0, kLinRR - 1);
+        const float wy1 = fy - (float)y0, wy0 = 1.0f - wy1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            if (!vx[kx]) continue;
+            constexpr int dummy = 0; (void)dummy;
+            const int tap = ky * 3 + kx;
+            // bilinear(P_tap) at the tap's pixel
+            const float w00 = wy0 * wx0[kx], w01 = wy0 * wx1[kx], w10 = wy1 * wx0[kx], w11 = wy1 * wx1[kx];
+            const float* p00 = Ps + (r0 * kLinRC + cx0[kx]) * PS + tap * CO;
+            const float* p01 = Ps + (r0 * kLinRC + cx1[kx]) * PS + tap * CO;
+            const float* p10 = Ps + (r1 * kLinRC + cx0[kx]) * PS + tap * CO;
+            const float* p11 = Ps + (r1 * kLinRC + cx1[kx]) * PS + tap * CO;
+#pragma unroll
+            for (int q = 0; q < CO; q += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(p00 + q), bq = *reinterpret_cast<const float4*>(p01 + q);
+                const float4 c = *reinterpret_cast<const float4*>(p10 + q), d = *reinterpret_cast<const float4*>(p11 + q);
+                acc[q + 0] = fmaf(w00, a.x, fmaf(w01, bq.x, fmaf(w10, c.x, fmaf(w11, d.x, acc[q + 0]))));
+                acc[q + 1] = fmaf(w00, a.y, fmaf(w01, bq.y, fmaf(w10, c.y, fmaf(w11, d.y, acc[q + 1]))));
+                acc[q + 2] = fmaf(w00, a.z, fmaf(w01, bq.z, fmaf(w10, c.z, fmaf(w11, d.z, acc[q + 2]))));
+                acc[q + 3] = fmaf(w00, a.w, fmaf(w01, bq.w, fmaf(w10, c.w, fmaf(w11, d.w, acc[q + 3]))));
+            }
+            // composed lateral convolution + bias term of this tap
+            const float* lp = Ls + (py + ky) * kLinLW + px + kx;
+#pragma unroll
+            for (int ci = 0; ci < CL; ++ci) {
+                const float v = lp[ci * kLinLH * kLinLW];
+#pragma unroll
+                for (int co = 0; co < CO; ++co) acc[co] = fmaf(p.wc[(tap * CL + ci) * CO + co], v, acc[co]);
+            }
+#pragma unroll
+            for (int co = 0; co < CO; ++co) acc[co] += p.bc[tap * CO + co];
+        }
+    }
+
+    const size_t fo = (((size_t)b * H + y) * W + x) * CO;
+    if constexpr (sizeof(OutT) == 4) {
+        float* fp = static_cast<float*>(p.feat) + fo;
+#pragma unroll
+        for (int q = 0; q < CO; q += 4)
+            *reinterpret_cast<float4*>(fp + q) = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+    } else {  // bf16, round to nearest even as torch's .to(bfloat16): 8 channels = one 16-byte store
+        __nv_bfloat16* fp = static_cast<__nv_bfloat16*>(p.feat) + fo;
+#pragma unroll
+        for (int q = 0; q < CO; q += 8) {
+            uint4 v;
+            v.x = lin_pack_bf16x2(acc[q], acc[q + 1]);
+            v.y = lin_pack_bf16x2(acc[q + 2], acc[q + 3]);
+            v.z = lin_pack_bf16x2(acc[q + 4], acc[q + 5]);
+            v.w = lin_pack_bf16x2(acc[q + 6], acc[q + 7]);
+            *reinterpret_cast<uint4*>(fp + q) = v;
+        }
+    }
+}
+
+template <int CL, int CO, typename OutT>
+static int launch_lin(const float* P, const float* lat, void* feat, const float* wc, const float* bc, int B, int H,
+                      int W, cudaStream_t s) {
+    static thread_local LinParams<CL, CO> p;
+    static_assert(sizeof(LinParams<CL, CO>) <= 32000, "weights must fit the kernel-parameter space");
+    memcpy(p.wc, wc, sizeof(p.wc));
+    memcpy(p.bc, bc, sizeof(p.bc));
+    p.P = P; p.lat = lat; p.feat = feat; p.B = B; p.H = H; p.W = W;
+    const int Hl = H / 2, Wl = W / 2;
+    p.sy = H > 1 ? (float)(Hl - 1) / (float)(H - 1) : 0.f;  // ATen area_pixel_compute_scale, align_corners=True
+    p.sx = W > 1 ? (float)(Wl - 1) / (float)(W - 1) : 0.f;
+    constexpr int SMEM = LinGeom<CL, CO>::SMEM;
+    static int attr_done[64] = {};  // largest size set per device
+    const int st = ensure_dynamic_smem_bytes(fpn_lin_kernel<CL, CO, OutT>, SMEM, attr_done, "fpn_topdown_lin: cudaFuncSetAttribute");
+    if (st != MVSTER_OK) return st;
+    dim3 grid((W + kLinTW - 1) / kLinTW, (H + kLinTH - 1) / kLinTH, B);
+    if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "fpn_topdown_lin: grid too large");
+    fpn_lin_kernel<CL, CO, OutT><<<grid, kLinThreads, SMEM, s>>>(p);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("fpn_topdown_lin launch");
+    return MVSTER_OK;
+}
+
+}  // namespace mvster
+
+using namespace mvster;
+
+extern "C" int mvster_fpn_topdown_lin(const float* P, const float* lat, void* feat, int feat_dtype,
+                                      const float* wc_host, const float* bc_host, int B, int Clat, int Cout, int H,
+                                      int W, void* stream) {
+    if (!P || !lat || !feat || !wc_host || !bc_host) return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown_lin: null pointer");
+    if (feat_dtype != MVSTER_F32 && feat_dtype != MVSTER_BF16)
+        return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown_lin: feat_dtype must be MVSTER_F32 or MVSTER_BF16");
+    if (B <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1))
+        return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown_lin: H, W must be even and >= 2");
+    if (((uintptr_t)feat) % 16 || ((uintptr_t)P) % 16) return fail(MVSTER_ERR_ALIGN, "fpn_topdown_lin: P and feat must be 16-byte aligned");
+    DeviceGuard guard(feat);
+    if (guard.status != MVSTER_OK) return guard.status;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool bf = feat_dtype == MVSTER_BF16;
+#define MVSTER_LIN_ARGS P, lat, feat, wc_host, bc_host, B, H, W, s
+    if (Clat == 8 && Cout == 8)
+        return bf ? launch_lin<8, 8, __nv_bfloat16>(MVSTER_LIN_ARGS) : launch_lin<8, 8, float>(MVSTER_LIN_ARGS);
+    if (Clat == 16 && Cout == 16)
+        return bf ? launch_lin<16, 16, __nv_bfloat16>(MVSTER_LIN_ARGS) : launch_lin<16, 16, float>(MVSTER_LIN_ARGS);
+#undef MVSTER_LIN_ARGS
+    return fail(MVSTER_ERR_UNSUPPORTED, "fpn_topdown_lin: no kernel for Clat=%d Cout=%d (built: (8,8), (16,16))", Clat, Cout);
+}

@@ -106,6 +106,7 @@ class FPN4(_FoldedWeights, nn.Module):
         self.out4 = nn.Conv2d(top, c, 3, padding=1, bias=False)
         self.out_channels = [8 * c, 4 * c, 2 * c, c]
         self.direct_convs = True  # eval: hand-written kernels for the encoder and the two finest top-down levels
+        self.linear_topdown = True  # finest top-down level via ops.fpn_topdown_lin (False: ops.fpn_topdown)
         self._fold_cache = {}
 
     # ---- eval-mode path on the hand-written kernels ---------------------------------------------------------------
@@ -134,6 +135,24 @@ class FPN4(_FoldedWeights, nn.Module):
             slices = [w[..., i * 8:(i + 1) * 8].contiguous() for i in range(out_conv.out_channels // 8)]
             w_in = inner.weight.detach()[:, :, 0, 0].t().contiguous().float().cpu()             # [cl, c64]
             hit = (key, slices, w_in, inner.bias.detach().float().cpu().contiguous())
+            self._fold_cache[tag] = hit
+        return hit[1], hit[2], hit[3]
+
+    def _topdown_lin_weights(self, out_conv: nn.Conv2d, inner: nn.Conv2d, tag: str, device):
+        """Weights of ``ops.fpn_topdown_lin``: the tap-wise projection of the coarser ``intra`` (device), the output
+        convolution composed with the lateral 1x1 convolution and with its bias (host, composed in float64)."""
+        key = (out_conv.weight._version, inner.weight._version, inner.bias._version, out_conv.weight.data_ptr(),
+               str(device))
+        hit = self._fold_cache.get(tag)
+        if hit is None or hit[0] != key:
+            w = out_conv.weight.detach().double().cpu()                          # [co, c64, ky, kx]
+            co = w.shape[0]
+            wt = w.permute(2, 3, 0, 1).reshape(9, co, 64)                        # [tap, co, c64]
+            wi = inner.weight.detach().double().cpu()[:, :, 0, 0]                # [c64, cl]
+            wp_t = wt.reshape(9 * co, 64).t().contiguous().float().to(device)    # [c64, tap*co]
+            wc = torch.matmul(wt, wi).permute(0, 2, 1).contiguous().float()      # [tap, cl, co]
+            bc = torch.matmul(wt, inner.bias.detach().double().cpu()).contiguous().float()   # [tap, co]
+            hit = (key, wp_t, wc, bc)
             self._fold_cache[tag] = hit
         return hit[1], hit[2], hit[3]
 
@@ -202,8 +221,12 @@ class FPN4(_FoldedWeights, nn.Module):
         out["stage2"] = ops.to_nhwc(feat2, fdt).permute(0, 3, 1, 2)
         w3, wi3, bi3 = self._topdown_weights(self.out3, self.inner2, "td3")
         feat3, intra3 = ops.fpn_topdown(intra2, c1, w3, wi3, bi3, want_intra=True, feature_dtype=fdt)
-        w4, wi4, bi4 = self._topdown_weights(self.out4, self.inner3, "td4")
-        feat4, _ = ops.fpn_topdown(intra3, c0, w4, wi4, bi4, want_intra=False, feature_dtype=fdt)
+        if self.linear_topdown:   # finest level through its linearity: no 64-channel full-resolution intra at all
+            wp4, wc4, bc4 = self._topdown_lin_weights(self.out4, self.inner3, "td4lin", x.device)
+            feat4 = ops.fpn_topdown_lin(intra3, c0, wp4, wc4, bc4, feature_dtype=fdt)
+        else:
+            w4, wi4, bi4 = self._topdown_weights(self.out4, self.inner3, "td4")
+            feat4, _ = ops.fpn_topdown(intra3, c0, w4, wi4, bi4, want_intra=False, feature_dtype=fdt)
         out["stage3"] = feat3.permute(0, 3, 1, 2)
         out["stage4"] = feat4.permute(0, 3, 1, 2)
         return out

@@ -550,6 +550,39 @@ def fpn_topdown(prev: torch.Tensor, lat: torch.Tensor, w_out_slices: Sequence[to
     return feat, intra
 
 
+def fpn_topdown_lin(prev: torch.Tensor, lat: torch.Tensor, wp_t: torch.Tensor, wc_host: torch.Tensor,
+                    bc_host: torch.Tensor, feature_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """One FPN4 top-down level through its linearity (``mvster_fpn_topdown_lin``), for a level whose ``intra`` no finer
+    level needs.  ``prev`` [B,64,H/2,W/2], ``lat`` [B,Clat,H,W] planar CUDA fp32; ``wp_t`` [64, 9*Cout] CUDA
+    (``wp_t[c, tap*Cout+co] = out_conv.weight[co,c,tap]``); ``wc_host`` [9,Clat,Cout], ``bc_host`` [9,Cout] CPU fp32.
+    Returns ``feat`` NHWC [B,H,W,Cout].  The 64 -> 9*Cout projection of ``prev`` is one fp32 cuBLAS GEMM (TF32 off)."""
+    _require_cuda(prev, "prev")
+    feature_dtype = feature_dtype or torch.float32
+    if feature_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("fpn_topdown_lin: feature dtype must be float32 or bfloat16")
+    prev, lat = _f32c(prev, "prev"), _f32c(lat, "lat")
+    b, clat, h, w = lat.shape
+    if tuple(prev.shape) != (b, 64, h // 2, w // 2) or h % 2 or w % 2 or h < 2 or w < 2:
+        raise RuntimeError("fpn_topdown_lin: prev %s does not match lat %s" % (tuple(prev.shape), tuple(lat.shape)))
+    cout = wp_t.shape[1] // 9
+    if tuple(wp_t.shape) != (64, 9 * cout) or wp_t.device != lat.device or wp_t.dtype != torch.float32:
+        raise RuntimeError("fpn_topdown_lin: wp_t must be fp32 [64, 9*Cout] on the features' device")
+    for t, shape in ((wc_host, (9, clat, cout)), (bc_host, (9, cout))):
+        if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise RuntimeError("fpn_topdown_lin: wc / bc must be contiguous CPU fp32 [9,Clat,Cout] / [9,Cout]")
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        proj = torch.matmul(prev.flatten(2).transpose(1, 2), wp_t)   # [B, H/2*W/2, 9*Cout] = NHWC
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    feat = torch.empty((b, h, w, cout), device=lat.device, dtype=feature_dtype)
+    _lib.check(_lib.load().mvster_fpn_topdown_lin(
+        _ptr(proj), _ptr(lat), _ptr(feat), _dtype_code(feat), ctypes.c_void_p(wc_host.data_ptr()),
+        ctypes.c_void_p(bc_host.data_ptr()), b, clat, cout, h, w, _stream(lat)))
+    return feat
+
+
 def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:
     b, d, h, w = attn.shape
     g_attn = None if g_attn is None else _f32c(g_attn, "grad attn")

@@ -1,6 +1,6 @@
 #!/bin/bash
-# one iteration on the GPU box: K1 parity tests (incl. the option variants), then the K2b A/B
+# one iteration on the GPU box: network tests, then the FPN A/B
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_parity.log 2>&1; echo "parity exit $?"; tail -5 gpurun_out/pytest_parity.log
-bash scripts/gpu_filter_ab.sh
+timeout 900 python -m pytest tests/test_gpu_network.py -m gpu -x -q > gpurun_out/pytest_network.log 2>&1; echo "network exit $?"; tail -5 gpurun_out/pytest_network.log
+timeout 600 python scripts/bench_fpn.py > gpurun_out/bench_fpn.log 2> gpurun_out/bench_fpn.err; echo "bench_fpn exit $?"; tail -1 gpurun_out/bench_fpn.log; tail -3 gpurun_out/bench_fpn.err

@@ -387,6 +387,50 @@ def test_fpn_topdown_matches_float64_torch(clat, cout, h, w, want_intra):
         assert got_intra is None
 
 
+@pytest.mark.parametrize("clat,cout,h,w", [(8, 8, 16, 64), (8, 8, 10, 70), (8, 8, 2, 2), (16, 16, 12, 36), (8, 8, 34, 130)])
+@pytest.mark.parametrize("fdt", [torch.float32, torch.bfloat16])
+def test_fpn_topdown_lin_matches_float64_torch(clat, cout, h, w, fdt):
+    """The linearised top-down level (projection GEMM at half resolution + bilinear gather + composed lateral
+    convolution) against up2 + inner + out_conv in float64: same 3e-5 bound as the direct evaluation; bf16 output is
+    the fp32 result rounded once."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(clat + cout + h + w)
+    prev = rng.normal(0, 1, (2, 64, h // 2, w // 2)).astype(np.float32)
+    lat = rng.normal(0, 1, (2, clat, h, w)).astype(np.float32)
+    w_out = rng.normal(0, 0.05, (cout, 64, 3, 3)).astype(np.float32)
+    w_in = rng.normal(0, 0.3, (64, clat, 1, 1)).astype(np.float32)
+    b_in = rng.normal(0, 0.2, 64).astype(np.float32)
+    pd, ld = torch.from_numpy(prev).double(), torch.from_numpy(lat).double()
+    intra = F.interpolate(pd, scale_factor=2, mode="bilinear", align_corners=True) + \
+        F.conv2d(ld, torch.from_numpy(w_in).double(), torch.from_numpy(b_in).double())
+    ref = F.conv2d(intra, torch.from_numpy(w_out).double(), padding=1)
+    wt = torch.from_numpy(w_out).double().permute(2, 3, 0, 1).reshape(9, cout, 64)
+    wp_t = wt.reshape(9 * cout, 64).t().contiguous().float().to(DEV)
+    wc = torch.matmul(wt, torch.from_numpy(w_in[:, :, 0, 0]).double()).permute(0, 2, 1).contiguous().float()
+    bc = torch.matmul(wt, torch.from_numpy(b_in).double()).contiguous().float()
+    feat = ops.fpn_topdown_lin(torch.from_numpy(prev).to(DEV), torch.from_numpy(lat).to(DEV), wp_t, wc, bc, fdt)
+    assert tuple(feat.shape) == (2, h, w, cout) and feat.dtype == fdt
+    if fdt == torch.bfloat16:
+        f32 = ops.fpn_topdown_lin(torch.from_numpy(prev).to(DEV), torch.from_numpy(lat).to(DEV), wp_t, wc, bc)
+        assert torch.equal(feat, f32.to(torch.bfloat16))
+        return
+    err = (feat.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+
+
+def test_fpn4_linear_and_direct_topdown_agree(golden, model):
+    g = golden("network")
+    x = torch.from_numpy(g["imgs"][1]).to(DEV)
+    outs = []
+    for lin in (True, False):
+        model.feature.linear_topdown = lin
+        with torch.no_grad():
+            outs.append(model.feature.forward_direct(x)["stage4"].clone())
+    model.feature.linear_topdown = True
+    ref = g["fpn_view1_stage4"]
+    assert (outs[0] - outs[1]).abs().max().item() < 2e-5 * max(1.0, float(np.abs(ref).max()))
+
+
 def test_fpn4_direct_path_matches_reference_golden(golden, model):
     g = golden("network")
     x = torch.from_numpy(g["imgs"][1]).to(DEV)
