@@ -34,10 +34,11 @@ template <int CL, int CO>
 struct LinParams {
     float wc[9 * CL * CO];  // [tap][ci][co]  composed W[tap] Wi
     float bc[9 * CO];       // [tap][co]      W[tap] bi
-    const float* P;         // [B, H/2, W/2, 9*CO] NHWC: P[.., tap*CO + co] = sum_c W[co,c,tap] prev[c]
+    const float* P;         // [B, H/2, W/2, pc] NHWC: P[.., poff + tap*CO + co] = sum_c W[co,c,tap] prev[c]
     const float* lat;       // [B, CL, H, W] planar
     void* feat;             // [B, H, W, CO] NHWC, fp32 or bf16
     int B, H, W;
+    int pc, poff;           // channels per coarse pixel of P (>= 9*CO, multiple of 4) and first channel used
     float sy, sx;           // align_corners=True source scale (Hl-1)/(H-1), (Wl-1)/(W-1)
 };
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kLinThreads, (CO == 8) ? 3 : 2) fpn_lin_kernel
             const int r = i / per_row, rem = i - r * per_row;
             const int c = rem / Q, j = rem - c * Q;
             const float4 v = __ldg(reinterpret_cast<const float4*>(
-                p.P + (((size_t)b * Hl + ly0 + r) * Wl + lx0) * PC) + rem);
+                p.P + (((size_t)b * Hl + ly0 + r) * Wl + lx0 + c) * p.pc + p.poff) + j);
             *reinterpret_cast<float4*>(Ps + (r * kLinRC + c) * PS + 4 * j) = v;
         }
         constexpr int LHW = kLinLH * (kLinTW + 2);
@@ -175,13 +176,13 @@ __global__ void __launch_bounds__(kLinThreads, (CO == 8) ? 3 : 2) fpn_lin_kernel
 }
 
 template <int CL, int CO, typename OutT>
-static int launch_lin(const float* P, const float* lat, void* feat, const float* wc, const float* bc, int B, int H,
-                      int W, cudaStream_t s) {
+static int launch_lin(const float* P, int pc, int poff, const float* lat, void* feat, const float* wc, const float* bc,
+                      int B, int H, int W, cudaStream_t s) {
     static thread_local LinParams<CL, CO> p;
     static_assert(sizeof(LinParams<CL, CO>) <= 32000, "weights must fit the kernel-parameter space");
     memcpy(p.wc, wc, sizeof(p.wc));
     memcpy(p.bc, bc, sizeof(p.bc));
-    p.P = P; p.lat = lat; p.feat = feat; p.B = B; p.H = H; p.W = W;
+    p.P = P; p.lat = lat; p.feat = feat; p.B = B; p.H = H; p.W = W; p.pc = pc; p.poff = poff;
     const int Hl = H / 2, Wl = W / 2;
     p.sy = H > 1 ? (float)(Hl - 1) / (float)(H - 1) : 0.f;  // ATen area_pixel_compute_scale, align_corners=True
     p.sx = W > 1 ? (float)(Wl - 1) / (float)(W - 1) : 0.f;
@@ -197,24 +198,112 @@ static int launch_lin(const float* P, const float* lat, void* feat, const float*
     return MVSTER_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Projection of an `intra` that is itself a top-down result, without forming it: with intra = up2(prev) + Wi lat + bi,
+//     P = Wp intra = up2(Wp prev) + (Wp Wi) lat + Wp bi                      (NP = 9 * Cout of the NEXT level channels)
+// Q = Wp prev comes from the caller's GEMM at the coarser resolution (NHWC, channels q_off .. q_off + NP - 1 of a pixel
+// of NQ channels); a thread owns one pixel and all NP channels: CL x NP lateral FMAs with uniform constant weights, four
+// bilinear taps of NP contiguous floats, NP contiguous floats out.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int CL, int NP>
+struct ProjUpParams {
+    float wl[CL * NP];  // [ci][n]  Wp Wi
+    float bl[NP];       //          Wp bi
+    const float* Q;     // [B, H/2, W/2, NQ] NHWC
+    const float* lat;   // [B, CL, H, W] planar
+    float* P;           // [B, H, W, NP] NHWC
+    int B, H, W, NQ, q_off;
+    float sy, sx;
+};
+
+template <int CL, int NP>
+__global__ void __launch_bounds__(128) fpn_proj_up_kernel(const __grid_constant__ ProjUpParams<CL, NP> p) {
+    const int H = p.H, W = p.W, Hl = H / 2, Wl = W / 2;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    float acc[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[n] = p.bl[n];
+    const float* lp = p.lat + ((size_t)b * CL * H + y) * W + x;
+#pragma unroll
+    for (int ci = 0; ci < CL; ++ci) {
+        const float v = __ldg(lp + (size_t)ci * H * W);
+#pragma unroll
+        for (int n = 0; n < NP; ++n) acc[n] = fmaf(p.wl[ci * NP + n], v, acc[n]);
+    }
+    // bilinear x2, align_corners=True (ATen: source = scale * dst)
+    const float fy = p.sy * (float)y, fx = p.sx * (float)x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hl - 1), x1 = x0 + (x0 < Wl - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float w00 = (1.0f - ly) * (1.0f - lx), w01 = (1.0f - ly) * lx, w10 = ly * (1.0f - lx), w11 = ly * lx;
+    const float* qb = p.Q + (size_t)b * Hl * Wl * p.NQ + p.q_off;
+    const float4* q00 = reinterpret_cast<const float4*>(qb + ((size_t)y0 * Wl + x0) * p.NQ);
+    const float4* q01 = reinterpret_cast<const float4*>(qb + ((size_t)y0 * Wl + x1) * p.NQ);
+    const float4* q10 = reinterpret_cast<const float4*>(qb + ((size_t)y1 * Wl + x0) * p.NQ);
+    const float4* q11 = reinterpret_cast<const float4*>(qb + ((size_t)y1 * Wl + x1) * p.NQ);
+    float4* op = reinterpret_cast<float4*>(p.P + (((size_t)b * H + y) * W + x) * NP);
+#pragma unroll
+    for (int j = 0; j < NP / 4; ++j) {
+        const float4 a = __ldg(q00 + j), bq = __ldg(q01 + j), c = __ldg(q10 + j), d = __ldg(q11 + j);
+        float4 o;
+        o.x = fmaf(w00, a.x, fmaf(w01, bq.x, fmaf(w10, c.x, fmaf(w11, d.x, acc[4 * j + 0]))));
+        o.y = fmaf(w00, a.y, fmaf(w01, bq.y, fmaf(w10, c.y, fmaf(w11, d.y, acc[4 * j + 1]))));
+        o.z = fmaf(w00, a.z, fmaf(w01, bq.z, fmaf(w10, c.z, fmaf(w11, d.z, acc[4 * j + 2]))));
+        o.w = fmaf(w00, a.w, fmaf(w01, bq.w, fmaf(w10, c.w, fmaf(w11, d.w, acc[4 * j + 3]))));
+        op[j] = o;
+    }
+}
+
 }  // namespace mvster
 
 using namespace mvster;
 
-extern "C" int mvster_fpn_topdown_lin(const float* P, const float* lat, void* feat, int feat_dtype,
-                                      const float* wc_host, const float* bc_host, int B, int Clat, int Cout, int H,
-                                      int W, void* stream) {
+extern "C" int mvster_fpn_project_up(const float* Q, int q_channels, int q_off, const float* lat, float* P,
+                                     const float* wl_host, const float* bl_host, int B, int Clat, int NP, int H, int W,
+                                     void* stream) {
+    if (!Q || !lat || !P || !wl_host || !bl_host) return fail(MVSTER_ERR_BAD_ARG, "fpn_project_up: null pointer");
+    if (B <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1))
+        return fail(MVSTER_ERR_BAD_ARG, "fpn_project_up: H, W must be even and >= 2");
+    if (q_off < 0 || q_off + NP > q_channels || (q_off & 3) || (q_channels & 3))
+        return fail(MVSTER_ERR_BAD_ARG, "fpn_project_up: bad channel window of Q");
+    if (((uintptr_t)Q) % 16 || ((uintptr_t)P) % 16) return fail(MVSTER_ERR_ALIGN, "fpn_project_up: Q and P must be 16-byte aligned");
+    if (Clat != 16 || NP != 72)
+        return fail(MVSTER_ERR_UNSUPPORTED, "fpn_project_up: no kernel for Clat=%d NP=%d (built: (16,72))", Clat, NP);
+    DeviceGuard guard(P);
+    if (guard.status != MVSTER_OK) return guard.status;
+    static thread_local ProjUpParams<16, 72> p;
+    memcpy(p.wl, wl_host, sizeof(p.wl));
+    memcpy(p.bl, bl_host, sizeof(p.bl));
+    p.Q = Q; p.lat = lat; p.P = P; p.B = B; p.H = H; p.W = W; p.NQ = q_channels; p.q_off = q_off;
+    p.sy = (float)(H / 2 - 1) / (float)(H - 1);
+    p.sx = (float)(W / 2 - 1) / (float)(W - 1);
+    dim3 grid((W + 31) / 32, (H + 3) / 4, B);
+    if (grid.y > 65535u || grid.z > 65535u) return fail(MVSTER_ERR_UNSUPPORTED, "fpn_project_up: grid too large");
+    fpn_proj_up_kernel<16, 72><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    count_launch();
+    MVSTER_CHECK_LAUNCH("fpn_project_up launch");
+    return MVSTER_OK;
+}
+
+extern "C" int mvster_fpn_topdown_lin(const float* P, int p_channels, int p_off, const float* lat, void* feat,
+                                      int feat_dtype, const float* wc_host, const float* bc_host, int B, int Clat,
+                                      int Cout, int H, int W, void* stream) {
     if (!P || !lat || !feat || !wc_host || !bc_host) return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown_lin: null pointer");
     if (feat_dtype != MVSTER_F32 && feat_dtype != MVSTER_BF16)
         return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown_lin: feat_dtype must be MVSTER_F32 or MVSTER_BF16");
     if (B <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1))
         return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown_lin: H, W must be even and >= 2");
     if (((uintptr_t)feat) % 16 || ((uintptr_t)P) % 16) return fail(MVSTER_ERR_ALIGN, "fpn_topdown_lin: P and feat must be 16-byte aligned");
+    if (p_off < 0 || p_off + 9 * Cout > p_channels || (p_off & 3) || (p_channels & 3))
+        return fail(MVSTER_ERR_BAD_ARG, "fpn_topdown_lin: bad channel window of P");
     DeviceGuard guard(feat);
     if (guard.status != MVSTER_OK) return guard.status;
     cudaStream_t s = (cudaStream_t)stream;
     const bool bf = feat_dtype == MVSTER_BF16;
-#define MVSTER_LIN_ARGS P, lat, feat, wc_host, bc_host, B, H, W, s
+#define MVSTER_LIN_ARGS P, p_channels, p_off, lat, feat, wc_host, bc_host, B, H, W, s
     if (Clat == 8 && Cout == 8)
         return bf ? launch_lin<8, 8, __nv_bfloat16>(MVSTER_LIN_ARGS) : launch_lin<8, 8, float>(MVSTER_LIN_ARGS);
     if (Clat == 16 && Cout == 16)

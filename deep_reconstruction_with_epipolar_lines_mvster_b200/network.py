@@ -106,7 +106,7 @@ class FPN4(_FoldedWeights, nn.Module):
         self.out4 = nn.Conv2d(top, c, 3, padding=1, bias=False)
         self.out_channels = [8 * c, 4 * c, 2 * c, c]
         self.direct_convs = True  # eval: hand-written kernels for the encoder and the two finest top-down levels
-        self.linear_topdown = True  # finest top-down level via ops.fpn_topdown_lin (False: ops.fpn_topdown)
+        self.linear_topdown = True  # the two finest top-down levels in linearised form (False: ops.fpn_topdown)
         self._fold_cache = {}
 
     # ---- eval-mode path on the hand-written kernels ---------------------------------------------------------------
@@ -138,23 +138,34 @@ class FPN4(_FoldedWeights, nn.Module):
             self._fold_cache[tag] = hit
         return hit[1], hit[2], hit[3]
 
-    def _topdown_lin_weights(self, out_conv: nn.Conv2d, inner: nn.Conv2d, tag: str, device):
-        """Weights of ``ops.fpn_topdown_lin``: the tap-wise projection of the coarser ``intra`` (device), the output
-        convolution composed with the lateral 1x1 convolution and with its bias (host, composed in float64)."""
-        key = (out_conv.weight._version, inner.weight._version, inner.bias._version, out_conv.weight.data_ptr(),
-               str(device))
-        hit = self._fold_cache.get(tag)
+    def _topdown_lin_weights(self, device):
+        """Weights of the two finest top-down levels in their linearised form (``ops.fpn_lin_gather`` /
+        ``ops.fpn_project_up``), composed in float64:
+        ``wq`` [64, 144+72] (device) projects ``intra2`` onto the taps of ``out3`` and of ``out4``;
+        per level ``wc`` [9,Clat,Cout] = W[tap] Wi and ``bc`` [9,Cout] = W[tap] bi (host);
+        ``wl`` [16,72] = Wp4 Wi2 and ``bl`` [72] = Wp4 b2 carry level 4's projection through level 3 (host)."""
+        convs = (self.out3, self.inner2, self.out4, self.inner3)
+        key = tuple(t._version for m in convs for t in m.parameters()) + (self.out3.weight.data_ptr(), str(device))
+        hit = self._fold_cache.get("tdlin")
         if hit is None or hit[0] != key:
-            w = out_conv.weight.detach().double().cpu()                          # [co, c64, ky, kx]
-            co = w.shape[0]
-            wt = w.permute(2, 3, 0, 1).reshape(9, co, 64)                        # [tap, co, c64]
-            wi = inner.weight.detach().double().cpu()[:, :, 0, 0]                # [c64, cl]
-            wp_t = wt.reshape(9 * co, 64).t().contiguous().float().to(device)    # [c64, tap*co]
-            wc = torch.matmul(wt, wi).permute(0, 2, 1).contiguous().float()      # [tap, cl, co]
-            bc = torch.matmul(wt, inner.bias.detach().double().cpu()).contiguous().float()   # [tap, co]
-            hit = (key, wp_t, wc, bc)
-            self._fold_cache[tag] = hit
-        return hit[1], hit[2], hit[3]
+            def level(out_conv, inner):
+                w = out_conv.weight.detach().double().cpu()                  # [co, c64, ky, kx]
+                co = w.shape[0]
+                wt = w.permute(2, 3, 0, 1).reshape(9, co, 64)                # [tap, co, c64]
+                wi = inner.weight.detach().double().cpu()[:, :, 0, 0]        # [c64, cl]
+                bi = inner.bias.detach().double().cpu()
+                wc = torch.matmul(wt, wi).permute(0, 2, 1).contiguous().float()   # [tap, cl, co]
+                bc = torch.matmul(wt, bi).contiguous().float()                    # [tap, co]
+                return wt.reshape(9 * co, 64), wc, bc
+            wp3, wc3, bc3 = level(self.out3, self.inner2)
+            wp4, wc4, bc4 = level(self.out4, self.inner3)
+            wi2 = self.inner2.weight.detach().double().cpu()[:, :, 0, 0]     # [c64, 16]
+            wl = torch.matmul(wp4, wi2).t().contiguous().float()             # [16, 72]
+            bl = torch.matmul(wp4, self.inner2.bias.detach().double().cpu()).contiguous().float()
+            wq = torch.cat([wp3, wp4], 0).t().contiguous().float().to(device)   # [64, 216]
+            hit = (key, dict(wq=wq, wc3=wc3, bc3=bc3, wc4=wc4, bc4=bc4, wl=wl, bl=bl, n3=wp3.shape[0], n4=wp4.shape[0]))
+            self._fold_cache["tdlin"] = hit
+        return hit[1]
 
     def direct_supported(self, x) -> bool:
         return (self.direct_convs and not self.training and self.base_channels == 8 and x.is_cuda
@@ -219,12 +230,17 @@ class FPN4(_FoldedWeights, nn.Module):
         else:
             feat2 = self.out2(intra2)
         out["stage2"] = ops.to_nhwc(feat2, fdt).permute(0, 3, 1, 2)
-        w3, wi3, bi3 = self._topdown_weights(self.out3, self.inner2, "td3")
-        feat3, intra3 = ops.fpn_topdown(intra2, c1, w3, wi3, bi3, want_intra=True, feature_dtype=fdt)
-        if self.linear_topdown:   # finest level through its linearity: no 64-channel full-resolution intra at all
-            wp4, wc4, bc4 = self._topdown_lin_weights(self.out4, self.inner3, "td4lin", x.device)
-            feat4 = ops.fpn_topdown_lin(intra3, c0, wp4, wc4, bc4, feature_dtype=fdt)
+        if self.linear_topdown:
+            # the two finest levels through their linearity: neither the half- nor the full-resolution 64-channel
+            # intra exists; one GEMM projects intra2 onto the taps of out3 and out4 (see fpn_lin.cu)
+            lw = self._topdown_lin_weights(x.device)
+            q = ops.fpn_project(intra2, lw["wq"])                                         # [B,H/4,W/4,144+72]
+            feat3 = ops.fpn_lin_gather(q, 0, c1, lw["wc3"], lw["bc3"], fdt)               # [B,H/2,W/2,16]
+            p4 = ops.fpn_project_up(q, lw["n3"], lw["n4"], c1, lw["wl"], lw["bl"])        # [B,H/2,W/2,72]
+            feat4 = ops.fpn_lin_gather(p4, 0, c0, lw["wc4"], lw["bc4"], fdt)              # [B,H,W,8]
         else:
+            w3, wi3, bi3 = self._topdown_weights(self.out3, self.inner2, "td3")
+            feat3, intra3 = ops.fpn_topdown(intra2, c1, w3, wi3, bi3, want_intra=True, feature_dtype=fdt)
             w4, wi4, bi4 = self._topdown_weights(self.out4, self.inner3, "td4")
             feat4, _ = ops.fpn_topdown(intra3, c0, w4, wi4, bi4, want_intra=False, feature_dtype=fdt)
         out["stage3"] = feat3.permute(0, 3, 1, 2)

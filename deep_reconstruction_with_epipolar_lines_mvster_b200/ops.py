@@ -550,37 +550,87 @@ def fpn_topdown(prev: torch.Tensor, lat: torch.Tensor, w_out_slices: Sequence[to
     return feat, intra
 
 
-def fpn_topdown_lin(prev: torch.Tensor, lat: torch.Tensor, wp_t: torch.Tensor, wc_host: torch.Tensor,
-                    bc_host: torch.Tensor, feature_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """One FPN4 top-down level through its linearity (``mvster_fpn_topdown_lin``), for a level whose ``intra`` no finer
-    level needs.  ``prev`` [B,64,H/2,W/2], ``lat`` [B,Clat,H,W] planar CUDA fp32; ``wp_t`` [64, 9*Cout] CUDA
-    (``wp_t[c, tap*Cout+co] = out_conv.weight[co,c,tap]``); ``wc_host`` [9,Clat,Cout], ``bc_host`` [9,Cout] CPU fp32.
-    Returns ``feat`` NHWC [B,H,W,Cout].  The 64 -> 9*Cout projection of ``prev`` is one fp32 cuBLAS GEMM (TF32 off)."""
-    _require_cuda(prev, "prev")
-    feature_dtype = feature_dtype or torch.float32
-    if feature_dtype not in (torch.float32, torch.bfloat16):
-        raise RuntimeError("fpn_topdown_lin: feature dtype must be float32 or bfloat16")
-    prev, lat = _f32c(prev, "prev"), _f32c(lat, "lat")
-    b, clat, h, w = lat.shape
-    if tuple(prev.shape) != (b, 64, h // 2, w // 2) or h % 2 or w % 2 or h < 2 or w < 2:
-        raise RuntimeError("fpn_topdown_lin: prev %s does not match lat %s" % (tuple(prev.shape), tuple(lat.shape)))
-    cout = wp_t.shape[1] // 9
-    if tuple(wp_t.shape) != (64, 9 * cout) or wp_t.device != lat.device or wp_t.dtype != torch.float32:
-        raise RuntimeError("fpn_topdown_lin: wp_t must be fp32 [64, 9*Cout] on the features' device")
-    for t, shape in ((wc_host, (9, clat, cout)), (bc_host, (9, cout))):
-        if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
-            raise RuntimeError("fpn_topdown_lin: wc / bc must be contiguous CPU fp32 [9,Clat,Cout] / [9,Cout]")
+def _matmul_fp32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """cuBLAS fp32 GEMM with TF32 off whatever the process-wide switch says (the FPN parity bounds are fp32 ones)."""
     tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        proj = torch.matmul(prev.flatten(2).transpose(1, 2), wp_t)   # [B, H/2*W/2, 9*Cout] = NHWC
+        return torch.matmul(a, b)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def fpn_project(intra: torch.Tensor, wp_t: torch.Tensor) -> torch.Tensor:
+    """``[B,64,h,w]`` planar -> ``[B,h,w,N]`` NHWC tap-wise projection ``intra^T wp_t`` (``wp_t`` [64,N] on the device):
+    the plain library GEMM in front of :func:`fpn_lin_gather` / :func:`fpn_project_up`."""
+    _require_cuda(intra, "intra")
+    intra = _f32c(intra, "intra")
+    b, c, h, w = intra.shape
+    if wp_t.dim() != 2 or wp_t.shape[0] != c or wp_t.device != intra.device or wp_t.dtype != torch.float32:
+        raise RuntimeError("fpn_project: wp_t must be fp32 [%d, N] on the features' device" % c)
+    return _matmul_fp32(intra.flatten(2).transpose(1, 2), wp_t).view(b, h, w, wp_t.shape[1])
+
+
+def fpn_lin_gather(proj: torch.Tensor, p_off: int, lat: torch.Tensor, wc_host: torch.Tensor, bc_host: torch.Tensor,
+                   feature_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``mvster_fpn_topdown_lin``: ``proj`` [B,H/2,W/2,Nc] NHWC fp32 (channels ``p_off .. p_off+9*Cout-1`` are this
+    level's tap-wise projection), ``lat`` [B,Clat,H,W] planar, ``wc_host`` [9,Clat,Cout], ``bc_host`` [9,Cout] CPU.
+    Returns ``feat`` NHWC [B,H,W,Cout] in ``feature_dtype`` (fp32 / bf16)."""
+    _require_cuda(lat, "lat")
+    feature_dtype = feature_dtype or torch.float32
+    if feature_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("fpn_topdown_lin: feature dtype must be float32 or bfloat16")
+    lat = _f32c(lat, "lat")
+    b, clat, h, w = lat.shape
+    if wc_host.dim() != 3 or bc_host.dim() != 2:
+        raise RuntimeError("fpn_topdown_lin: wc / bc must be [9,Clat,Cout] / [9,Cout]")
+    cout = wc_host.shape[2]
+    for t, shape in ((wc_host, (9, clat, cout)), (bc_host, (9, cout))):
+        if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise RuntimeError("fpn_topdown_lin: wc / bc must be contiguous CPU fp32 [9,Clat,Cout] / [9,Cout]")
+    if h % 2 or w % 2 or h < 2 or w < 2 or proj.dim() != 4 or tuple(proj.shape[:3]) != (b, h // 2, w // 2) \
+            or proj.dtype != torch.float32 or proj.device != lat.device or not proj.is_contiguous():
+        raise RuntimeError("fpn_topdown_lin: proj %s must be contiguous fp32 [B,H/2,W/2,N] matching lat %s"
+                           % (tuple(proj.shape), tuple(lat.shape)))
     feat = torch.empty((b, h, w, cout), device=lat.device, dtype=feature_dtype)
     _lib.check(_lib.load().mvster_fpn_topdown_lin(
-        _ptr(proj), _ptr(lat), _ptr(feat), _dtype_code(feat), ctypes.c_void_p(wc_host.data_ptr()),
-        ctypes.c_void_p(bc_host.data_ptr()), b, clat, cout, h, w, _stream(lat)))
+        _ptr(proj), int(proj.shape[3]), int(p_off), _ptr(lat), _ptr(feat), _dtype_code(feat),
+        ctypes.c_void_p(wc_host.data_ptr()), ctypes.c_void_p(bc_host.data_ptr()), b, clat, cout, h, w, _stream(lat)))
     return feat
+
+
+def fpn_project_up(q: torch.Tensor, q_off: int, n_proj: int, lat: torch.Tensor, wl_host: torch.Tensor,
+                   bl_host: torch.Tensor) -> torch.Tensor:
+    """``mvster_fpn_project_up``: the projection of ``up2(prev) + inner(lat)`` from ``q = project(prev)`` (NHWC
+    [B,H/2,W/2,Nq], channels ``q_off .. q_off+n_proj-1``): returns NHWC [B,H,W,n_proj] fp32."""
+    _require_cuda(lat, "lat")
+    lat = _f32c(lat, "lat")
+    b, clat, h, w = lat.shape
+    if h % 2 or w % 2 or h < 2 or w < 2 or q.dim() != 4 or tuple(q.shape[:3]) != (b, h // 2, w // 2) \
+            or q.dtype != torch.float32 or q.device != lat.device or not q.is_contiguous():
+        raise RuntimeError("fpn_project_up: q %s must be contiguous fp32 [B,H/2,W/2,N] matching lat %s"
+                           % (tuple(q.shape), tuple(lat.shape)))
+    for t, shape in ((wl_host, (clat, n_proj)), (bl_host, (n_proj,))):
+        if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise RuntimeError("fpn_project_up: wl / bl must be contiguous CPU fp32 [Clat,N] / [N]")
+    out = torch.empty((b, h, w, n_proj), device=lat.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_fpn_project_up(
+        _ptr(q), int(q.shape[3]), int(q_off), _ptr(lat), _ptr(out), ctypes.c_void_p(wl_host.data_ptr()),
+        ctypes.c_void_p(bl_host.data_ptr()), b, clat, int(n_proj), h, w, _stream(lat)))
+    return out
+
+
+def fpn_topdown_lin(prev: torch.Tensor, lat: torch.Tensor, wp_t: torch.Tensor, wc_host: torch.Tensor,
+                    bc_host: torch.Tensor, feature_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """One FPN4 top-down level through its linearity, for a level whose ``intra`` no finer level needs:
+    ``fpn_project`` (one fp32 cuBLAS GEMM, 64 -> 9*Cout at half resolution) + ``fpn_lin_gather``.
+    ``prev`` [B,64,H/2,W/2], ``lat`` [B,Clat,H,W] planar CUDA fp32; ``wp_t`` [64, 9*Cout] CUDA
+    (``wp_t[c, tap*Cout+co] = out_conv.weight[co,c,tap]``); ``wc_host`` [9,Clat,Cout], ``bc_host`` [9,Cout] CPU fp32.
+    Returns ``feat`` NHWC [B,H,W,Cout]."""
+    b, clat, h, w = lat.shape
+    if tuple(prev.shape) != (b, 64, h // 2, w // 2):
+        raise RuntimeError("fpn_topdown_lin: prev %s does not match lat %s" % (tuple(prev.shape), tuple(lat.shape)))
+    return fpn_lin_gather(fpn_project(prev, wp_t), 0, lat, wc_host, bc_host, feature_dtype)
 
 
 def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:

@@ -242,15 +242,22 @@ int mvster_fpn_topdown_ex(const float* prev, const float* lat, const float* intr
 
 /* mvster_fpn_topdown_lin: the same pyramid level (models/mvs4net_utils.py:488-495) evaluated through its linearity,
  *     feat[x] = sum_tap bilinear(P_tap)(x + tap) + sum_tap (W[tap] Wi) lat[x + tap] + sum_tap W[tap] bi   (taps inside the image)
- * without the 64-channel `intra` (not needed when no finer level follows):
- *   P     dev  [B,H/2,W/2,9*Cout] NHWC fp32: P[.., tap*Cout + co] = sum_c out_conv.weight[co,c,tap] prev[c] (a GEMM over
- *                                 the coarser level's intra, done by the caller)
+ * without the 64-channel `intra`:
+ *   P     dev  [B,H/2,W/2,p_channels] NHWC fp32; P[.., p_off + tap*Cout + co] = sum_c out_conv.weight[co,c,tap] prev[c]
+ *                                 (a GEMM over the coarser level's intra, done by the caller, or mvster_fpn_project_up)
  *   lat   dev  [B,Clat,H,W] planar encoder map
  *   feat  dev  [B,H,W,Cout] NHWC, feat_dtype MVSTER_F32 or MVSTER_BF16
  *   wc    HOST [9,Clat,Cout] composed lateral weights W[tap] Wi;  bc HOST [9,Cout] bias terms W[tap] bi
  * Compiled (Clat, Cout): (8,8), (16,16).  H, W even.  Differs from mvster_fpn_topdown by fp32 rounding only. */
-int mvster_fpn_topdown_lin(const float* P, const float* lat, void* feat, int feat_dtype, const float* wc,
-                           const float* bc, int B, int Clat, int Cout, int H, int W, void* stream);
+int mvster_fpn_topdown_lin(const float* P, int p_channels, int p_off, const float* lat, void* feat, int feat_dtype,
+                           const float* wc, const float* bc, int B, int Clat, int Cout, int H, int W, void* stream);
+
+/* mvster_fpn_project_up: the projection P = Wp intra of a level whose intra = up2(prev) + inner(lat) is not formed:
+ *     P[x] = bilinear(Q)(x) + (Wp Wi) lat[x] + Wp bi,     Q = Wp prev at the coarser resolution
+ *   Q   dev  [B,H/2,W/2,q_channels] NHWC (channels q_off .. q_off+NP-1 are used);  lat dev [B,Clat,H,W] planar
+ *   P   dev  [B,H,W,NP] NHWC;  wl HOST [Clat,NP];  bl HOST [NP].   Compiled (Clat, NP): (16,72). */
+int mvster_fpn_project_up(const float* Q, int q_channels, int q_off, const float* lat, float* P, const float* wl,
+                          const float* bl, int B, int Clat, int NP, int H, int W, void* stream);
 /* backward of the tail w.r.t. the logits: softmax backward of g_attn (+ the regression term of g_depth when
  * depth_mode == MVSTER_DEPTH_REGRESS); g_attn / g_depth may be NULL (treated as zero) */
 int mvster_tail_bwd(const float* attn, const float* hypo, const float* depth, const float* g_attn,

@@ -43,9 +43,10 @@ def main():
             feats[tag] = model.extract_features(imgs)
             out = model(imgs, proj, dv)
             res["depth_mean_%s" % tag] = float(out["stage4"]["depth"].mean())
-    f0, f1 = feats["direct"][0]["stage4"], feats["linear"][0]["stage4"]
-    res["stage4_feature_max_abs_diff"] = float((f0 - f1).abs().max())
-    res["stage4_feature_abs_max"] = float(f0.abs().max())
+    for k in ("stage3", "stage4"):
+        f0, f1 = feats["direct"][0][k], feats["linear"][0][k]
+        res[k + "_feature_max_abs_diff"] = float((f0 - f1).abs().max())
+        res[k + "_feature_abs_max"] = float(f0.abs().max())
     print(json.dumps(res))
 
 

@@ -418,6 +418,44 @@ def test_fpn_topdown_lin_matches_float64_torch(clat, cout, h, w, fdt):
     assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
 
 
+def test_fpn_project_up_matches_float64_torch():
+    """P = Wp (up2(prev) + inner(lat)) from Q = Wp prev, without intra (``mvster_fpn_project_up``), and the level that
+    consumes it, against the plain op sequence in float64."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(11)
+    h, w = 12, 40                                     # the middle level; the finest is 2h x 2w
+    prev = rng.normal(0, 1, (2, 64, h // 2, w // 2)).astype(np.float32)
+    lat = rng.normal(0, 1, (2, 16, h, w)).astype(np.float32)
+    lat_fine = rng.normal(0, 1, (2, 8, 2 * h, 2 * w)).astype(np.float32)
+    w_in = rng.normal(0, 0.3, (64, 16, 1, 1)).astype(np.float32)
+    b_in = rng.normal(0, 0.2, 64).astype(np.float32)
+    w_out4 = rng.normal(0, 0.05, (8, 64, 3, 3)).astype(np.float32)
+    w_in4 = rng.normal(0, 0.3, (64, 8, 1, 1)).astype(np.float32)
+    b_in4 = rng.normal(0, 0.2, 64).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).double()
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)
+    intra = up(d(prev)) + F.conv2d(d(lat), d(w_in), d(b_in))
+    wt4 = d(w_out4).permute(2, 3, 0, 1).reshape(72, 64)                                   # [tap*8+co, c64]
+    ref_p = torch.einsum("nc,bchw->bhwn", wt4, intra)
+    junk = rng.normal(0, 1, (64, 12)).astype(np.float32)                                  # other channels of Q
+    wq = torch.cat([torch.from_numpy(junk), wt4.t().float()], 1).contiguous().to(DEV)     # [64, 12 + 72]
+    q = ops.fpn_project(torch.from_numpy(prev).to(DEV), wq)
+    wl = torch.matmul(wt4, d(w_in[:, :, 0, 0])).t().contiguous().float()
+    bl = torch.matmul(wt4, d(b_in)).contiguous().float()
+    got_p = ops.fpn_project_up(q, 12, 72, torch.from_numpy(lat).to(DEV), wl, bl)
+    assert tuple(got_p.shape) == (2, h, w, 72)
+    assert (got_p.cpu().double() - ref_p).abs().max().item() < 2e-5 * max(1.0, ref_p.abs().max().item())
+    # ... and the finest level evaluated from it
+    ref = F.conv2d(up(intra) + F.conv2d(d(lat_fine), d(w_in4), d(b_in4)), d(w_out4), padding=1)
+    wc = torch.matmul(wt4.reshape(9, 8, 64), d(w_in4[:, :, 0, 0])).permute(0, 2, 1).contiguous().float()
+    bc = torch.matmul(wt4.reshape(9, 8, 64), d(b_in4)).contiguous().float()
+    feat = ops.fpn_lin_gather(got_p, 0, torch.from_numpy(lat_fine).to(DEV), wc, bc)
+    err = (feat.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+    with pytest.raises(RuntimeError):
+        ops.fpn_project_up(q, 10, 72, torch.from_numpy(lat).to(DEV), wl, bl)              # window not 16-byte aligned
+
+
 def test_fpn4_linear_and_direct_topdown_agree(golden, model):
     g = golden("network")
     x = torch.from_numpy(g["imgs"][1]).to(DEV)
@@ -425,10 +463,12 @@ def test_fpn4_linear_and_direct_topdown_agree(golden, model):
     for lin in (True, False):
         model.feature.linear_topdown = lin
         with torch.no_grad():
-            outs.append(model.feature.forward_direct(x)["stage4"].clone())
+            o = model.feature.forward_direct(x)
+            outs.append({k: o[k].clone() for k in ("stage3", "stage4")})
     model.feature.linear_topdown = True
-    ref = g["fpn_view1_stage4"]
-    assert (outs[0] - outs[1]).abs().max().item() < 2e-5 * max(1.0, float(np.abs(ref).max()))
+    for k in ("stage3", "stage4"):
+        ref = g["fpn_view1_" + k]
+        assert (outs[0][k] - outs[1][k]).abs().max().item() < 2e-5 * max(1.0, float(np.abs(ref).max())), k
 
 
 def test_fpn4_direct_path_matches_reference_golden(golden, model):
