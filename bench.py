@@ -293,8 +293,9 @@ def run_network(args, dev):
     return {"value": 1e3 / ms, "unit": UNIT, "ms_per_depth_map": ms,
             "workload": "MVS4net.forward, images in -> 4-stage depth out, %dx%d N=%d, one scene per call, fp32 "
                         "(cuDNN TF32 off)" % (h0, w0, n),
-            "what": "FPN4 + reg2d (hand-written direct / fused convolutions + cuDNN for the 32/64-channel layers) "
-                    "around the hot path; secondary number, not part of `value`"}
+            "what": "FPN4 + reg2d (hand-written direct / fused convolutions, tcgen05 implicit GEMMs for the "
+                    "32/64-channel layers, linearised FPN top-down behind one cuBLAS projection GEMM; cuDNN only for "
+                    "the 1x1 convolutions at 1/8 resolution) around the hot path; secondary number, not part of `value`"}
 
 
 def run_network_e2e(args, dev, barrier, world):
