@@ -166,24 +166,30 @@ __global__ void __launch_bounds__(256) schedule_inverse_range_kernel(const float
 
 // Same arithmetic, four consecutive pixels of a row per thread (W % 4 == 0): the eight low-resolution values a
 // pixel quad needs sit in at most three columns, and every hypothesis plane is written with one 16-byte store.
-__global__ void __launch_bounds__(256) schedule_inverse_range_x4_kernel(const float* __restrict__ inv_min,
+// 3-D grid (quad column, row, batch) and the D interpolation fractions d / (D - 1) as kernel parameters: the first
+// version derived (b, y, x) from a flat 64-bit index and divided d by D - 1 per thread and hypothesis - 805
+// instructions per thread, issue-bound at 30 % of the HBM write rate (profiles/r02_step_kernels_ncu.md).
+constexpr int kSchedMaxD = 32;
+struct ScheduleItv {
+    float v[kSchedMaxD];  // (float)d / (float)(D - 1), the reference's itv (models/mvs4net_utils.py:91)
+};
+__global__ void __launch_bounds__(128) schedule_inverse_range_x4_kernel(const float* __restrict__ inv_min,
                                                                         const float* __restrict__ inv_max,
-                                                                        float* __restrict__ hypo, int D, int H, int W,
-                                                                        int Hl, int Wl, float sy, float sx,
-                                                                        size_t total4 /* B*H*W/4 */) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total4) return;
+                                                                        float* __restrict__ hypo,
+                                                                        const __grid_constant__ ScheduleItv itv, int D,
+                                                                        int H, int W, int Hl, int Wl, float sy, float sx) {
     const int W4 = W >> 2;
-    const size_t plane = (size_t)H * W, plane4 = (size_t)H * W4;
-    const size_t b = i / plane4, r4 = i - b * plane4;
-    const int y = (int)(r4 / W4), xq = (int)(r4 - (size_t)y * W4) * 4;
+    const int q = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, b = blockIdx.z;
+    if (q >= W4 || y >= H) return;
+    const int xq = q * 4;
     const float fy = sy * (float)y;
     const int y0 = (int)fy, y1 = y0 + (y0 < Hl - 1);
     const float ly = fy - (float)y0, hy = 1.0f - ly;
-    const float* mx0 = inv_max + b * (size_t)Hl * Wl + (size_t)y0 * Wl;
-    const float* mx1 = inv_max + b * (size_t)Hl * Wl + (size_t)y1 * Wl;
-    const float* mn0 = inv_min + b * (size_t)Hl * Wl + (size_t)y0 * Wl;
-    const float* mn1 = inv_min + b * (size_t)Hl * Wl + (size_t)y1 * Wl;
+    const int lb = b * Hl * Wl;  // B * Hl * Wl < 2^31 (checked on the host)
+    const float* mx0 = inv_max + lb + y0 * Wl;
+    const float* mx1 = inv_max + lb + y1 * Wl;
+    const float* mn0 = inv_min + lb + y0 * Wl;
+    const float* mn1 = inv_min + lb + y1 * Wl;
     float m00[4], m01[4], m10[4], m11[4], d00[4], d01[4], d10[4], d11[4], lx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -194,16 +200,18 @@ __global__ void __launch_bounds__(256) schedule_inverse_range_x4_kernel(const fl
         d00[k] = __ldg(mn0 + x0) - m00[k]; d01[k] = __ldg(mn0 + x1) - m01[k];
         d10[k] = __ldg(mn1 + x0) - m10[k]; d11[k] = __ldg(mn1 + x1) - m11[k];
     }
-    float* out = hypo + b * D * plane + (size_t)y * W + xq;
+    const size_t plane = (size_t)H * W;
+    float* out = hypo + (size_t)b * D * plane + (size_t)y * W + xq;
     for (int d = 0; d < D; ++d) {
-        const float itv = (float)d / (float)(D - 1);
+        const float t = itv.v[d];
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float hx = 1.0f - lx[k];
-            const float v00 = m00[k] + d00[k] * itv, v01 = m01[k] + d01[k] * itv;
-            const float v10 = m10[k] + d10[k] * itv, v11 = m11[k] + d11[k] * itv;
-            o[k] = 1.0f / (hy * (hx * v00 + lx[k] * v01) + ly * (hx * v10 + lx[k] * v11));
+            const float v00 = m00[k] + d00[k] * t, v01 = m01[k] + d01[k] * t;
+            const float v10 = m10[k] + d10[k] * t, v11 = m11[k] + d11[k] * t;
+            // __frcp_rn is the correctly rounded reciprocal: the same value as the IEEE division 1.0f / v
+            o[k] = __frcp_rn(hy * (hx * v00 + lx[k] * v01) + ly * (hx * v10 + lx[k] * v11));
         }
         asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(out + (size_t)d * plane), "f"(o[0]), "f"(o[1]),
                      "f"(o[2]), "f"(o[3]) : "memory");
@@ -281,9 +289,13 @@ extern "C" int mvster_schedule_inverse_range(const float* inv_min, const float* 
     const float sy = H > 1 ? (float)(Hl - 1) / (float)(H - 1) : 0.f;
     const float sx = W > 1 ? (float)(Wl - 1) / (float)(W - 1) : 0.f;
     const size_t total = (size_t)B * H * W;
-    if (W % 4 == 0 && ((uintptr_t)hypo) % 16 == 0) {
-        schedule_inverse_range_x4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            inv_min, inv_max, hypo, D, H, W, Hl, Wl, sy, sx, total / 4);
+    if (W % 4 == 0 && ((uintptr_t)hypo) % 16 == 0 && D <= kSchedMaxD && B <= 65535 && (H + 3) / 4 <= 65535 &&
+        (double)B * Hl * Wl < 2147483648.0) {
+        ScheduleItv itv{};
+        for (int d = 0; d < D; ++d) itv.v[d] = (float)d / (float)(D - 1);
+        dim3 grid((W / 4 + 31) / 32, (H + 3) / 4, B);
+        schedule_inverse_range_x4_kernel<<<grid, dim3(32, 4), 0, (cudaStream_t)stream>>>(inv_min, inv_max, hypo, itv, D, H, W,
+                                                                                       Hl, Wl, sy, sx);
     } else {
         schedule_inverse_range_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
             inv_min, inv_max, hypo, D, H, W, Hl, Wl, sy, sx, total);
