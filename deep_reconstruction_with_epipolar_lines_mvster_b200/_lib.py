@@ -49,6 +49,10 @@ _SIGNATURES = {
     "mvster_fpn_topdown_ex": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, _P] + [c_int] * 7 + [_P]),
     "mvster_fpn_topdown_lin": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P] + [c_int] * 5 + [_P]),
     "mvster_fpn_project_up": (c_int, [_P, c_int, c_int, _P, _P, _P, _P] + [c_int] * 5 + [_P]),
+    "mvster_bn_train_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, ctypes.c_longlong]),
+    "mvster_bn_train_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_int, c_int,
+                                    ctypes.c_longlong, _P, _P]),
+    "mvster_bn_train_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, ctypes.c_longlong, _P, _P]),
     "mvster_tail_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "mvster_geo_check_pair": (c_int, [_P, POINTER(c_double), POINTER(c_double), _P, POINTER(c_double),
                                       POINTER(c_double), c_double, c_double, _P, _P, _P, _P, c_int, c_int, _P]),

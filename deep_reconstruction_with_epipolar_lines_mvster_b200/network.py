@@ -33,6 +33,43 @@ from .stagenet import init_inverse_range, schedule_inverse_range, stagenet
 # ----------------------------------------------------------------------------------------------------------------------
 # building blocks (parameter names follow the reference so that checkpoints load)
 # ----------------------------------------------------------------------------------------------------------------------
+class _BatchNormReLUTrain(torch.autograd.Function):
+    """``relu?(batch_norm(x))`` in training mode on ``ops.bn_train_fwd`` / ``ops.bn_train_bwd``: batch statistics, running
+    statistics updated in place, gradients to ``x``, ``weight`` and ``bias``.  Saves ``x``, the output and two [C] vectors
+    (autograd through ``F.relu(bn(x))`` keeps the same two activations)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
+        y, mean, invstd = ops.bn_train_fwd(x, weight, bias, running_mean, running_var, momentum, eps, relu)
+        ctx.save_for_backward(x, y, weight, mean, invstd)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        dx, dw, db = ops.bn_train_bwd(x, y, dy, weight, mean, invstd, ctx.relu)
+        return (dx if ctx.needs_input_grad[0] else None, dw if ctx.needs_input_grad[1] else None,
+                db if ctx.needs_input_grad[2] else None, None, None, None, None, None)
+
+
+def bn_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, relu: bool) -> torch.Tensor:
+    """``relu(bn(x))`` of the reference's conv blocks.  Training mode on planar fp32 CUDA activations (the regulariser's
+    [B,C,D,H,W] tensors) runs the fused B200 kernels; everything else (eval, channels_last, CPU, other dtypes,
+    ``track_running_stats=False`` / ``momentum=None`` modules) is the stock PyTorch computation."""
+    if (FUSED_TRAIN_BATCHNORM and bn.training and torch.is_grad_enabled() and bn.track_running_stats and bn.affine
+            and bn.momentum is not None and ops.bn_train_supported(x) and x[0, 0].numel() * x.shape[0] > 1):
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return _BatchNormReLUTrain.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum),
+                                         float(bn.eps), bool(relu))
+    y = bn(x)
+    return F.relu(y, inplace=True) if relu else y
+
+
+FUSED_TRAIN_BATCHNORM = True  # module switch (tests / A-B timing): False = stock nn.BatchNorm + F.relu in training
+
+
 class Conv2d(nn.Module):
     """conv -> BatchNorm2d -> ReLU (reference mvs4net_utils.py:231-258, the ``gn=False`` branch)."""
 
@@ -43,8 +80,7 @@ class Conv2d(nn.Module):
         self.relu = relu
 
     def forward(self, x):
-        x = self.bn(self.conv(x))
-        return F.relu(x, inplace=True) if self.relu else x
+        return bn_act(self.bn, self.conv(x), self.relu)
 
 
 class _FoldedWeights:
@@ -275,7 +311,7 @@ class ConvBnReLU3D(nn.Module):
         self.bn = nn.BatchNorm3d(cout)
 
     def forward(self, x):
-        return F.relu(self.bn(self.conv(x)), inplace=True)
+        return bn_act(self.bn, self.conv(x), True)
 
 
 def _up3d(cin, cout):
@@ -316,18 +352,23 @@ class reg2d(_FoldedWeights, nn.Module):
         self._fold_cache = {}
         self.direct_convs = True  # eval-mode fused path: hand-written direct convolutions where available
 
+    @staticmethod
+    def _up(seq: nn.Sequential, x):
+        """``_up3d`` block (ConvTranspose3d, BatchNorm3d, ReLU) with the BatchNorm + ReLU pair through ``bn_act``."""
+        return bn_act(seq[1], seq[0](x), True)
+
     def _trunk(self, x):
         conv0 = self.conv0(x)
         conv2 = self.conv2(self.conv1(conv0))
         conv4 = self.conv4(self.conv3(conv2))
         x = self.conv6(self.conv5(conv4))
-        x = conv4 + self.conv7(x)
-        x = conv2 + self.conv9(x)
+        x = conv4 + self._up(self.conv7, x)
+        x = conv2 + self._up(self.conv9, x)
         return conv0, x
 
     def forward(self, x):
         conv0, x = self._trunk(x)
-        x = conv0 + self.conv11(x)
+        x = conv0 + self._up(self.conv11, x)
         return self.prob(x).squeeze(1)
 
     # ---- fused last layers + tail -----------------------------------------------------------------------------------

@@ -633,6 +633,57 @@ def fpn_topdown_lin(prev: torch.Tensor, lat: torch.Tensor, wp_t: torch.Tensor, w
     return fpn_lin_gather(fpn_project(prev, wp_t), 0, lat, wc_host, bc_host, feature_dtype)
 
 
+def bn_train_supported(x: torch.Tensor) -> bool:
+    """Planar fp32 CUDA activations ``[N, C, ...]`` whose (sample, channel) plane is a multiple of four elements."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x.is_contiguous()):
+        return False
+    plane = x[0, 0].numel()
+    return plane > 0 and plane % 4 == 0 and x.shape[0] * x.shape[1] <= 65535 and x.data_ptr() % 16 == 0
+
+
+def _bn_workspace(n: int, c: int, s: int, dev) -> torch.Tensor:
+    nbytes = int(_lib.load().mvster_bn_train_workspace_bytes(n, c, s))
+    return torch.empty(((nbytes + 7) // 8,), device=dev, dtype=torch.float64)
+
+
+def bn_train_fwd(x: torch.Tensor, weight, bias, running_mean, running_var, momentum: float, eps: float, relu: bool):
+    """Training-mode BatchNorm (+ ReLU) forward (``mvster_bn_train_fwd``).  Returns ``(y, mean [C], invstd [C])`` and
+    updates ``running_mean`` / ``running_var`` in place like ``F.batch_norm(training=True)``."""
+    if not bn_train_supported(x):
+        raise RuntimeError("bn_train_fwd: needs a contiguous planar fp32 CUDA tensor [N,C,...] with a plane size % 4 == 0")
+    n, c = x.shape[0], x.shape[1]
+    s = x[0, 0].numel()
+    y = torch.empty_like(x)
+    mean = torch.empty((c,), device=x.device, dtype=torch.float32)
+    invstd = torch.empty_like(mean)
+    for t in (weight, bias, running_mean, running_var):
+        if t is not None and (t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != c):
+            raise RuntimeError("bn_train_fwd: weight / bias / running statistics must be contiguous fp32 [C] on x's device")
+    ws = _bn_workspace(n, c, s, x.device)
+    _lib.check(_lib.load().mvster_bn_train_fwd(
+        _ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(mean), _ptr(invstd), _ptr(running_mean), _ptr(running_var),
+        float(momentum), float(eps), int(bool(relu)), n, c, s, _ptr(ws), _stream(x)))
+    return y, mean, invstd
+
+
+def bn_train_bwd(x: torch.Tensor, y: torch.Tensor, dy: torch.Tensor, weight, mean: torch.Tensor, invstd: torch.Tensor,
+                 relu: bool):
+    """Training-mode BatchNorm (+ ReLU) backward (``mvster_bn_train_bwd``).  Returns ``(dx, dweight [C], dbias [C])``."""
+    n, c = x.shape[0], x.shape[1]
+    s = x[0, 0].numel()
+    dy = _f32c(dy, "grad_output")
+    if dy.shape != x.shape or dy.data_ptr() % 16:
+        raise RuntimeError("bn_train_bwd: grad_output must match x and be 16-byte aligned")
+    dx = torch.empty_like(x)
+    dw = torch.empty((c,), device=x.device, dtype=torch.float32)
+    db = torch.empty_like(dw)
+    ws = _bn_workspace(n, c, s, x.device)
+    _lib.check(_lib.load().mvster_bn_train_bwd(
+        _ptr(x), _ptr(y), _ptr(dy), _ptr(weight), _ptr(mean), _ptr(invstd), _ptr(dx), _ptr(dw), _ptr(db),
+        int(bool(relu)), n, c, s, _ptr(ws), _stream(x)))
+    return dx, dw, db
+
+
 def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:
     b, d, h, w = attn.shape
     g_attn = None if g_attn is None else _f32c(g_attn, "grad attn")

@@ -117,6 +117,23 @@ int mvster_epi_bwd_mode(const void* ref, const void* const* src, const float* rt
                         int C, int G, int D, int H, int W, int Hs, int Ws, float attn_temp, int dtype, int group_cor,
                         int attn_fuse_d, void* stream);
 
+/* ---- training-mode BatchNorm (+ ReLU) of the regulariser blocks ----------------------------------------------------
+ * nn.BatchNorm3d / nn.BatchNorm2d in train() followed by ReLU, as inside ConvBnReLU3D / Deconv3d / Conv2d
+ * (models/mvs4net_utils.py:123-130, 231-258, 884-926; autograd of the same in the backward), over PLANAR fp32
+ * activations x [N, C, S] (S = D*H*W or H*W contiguous, S % 4 == 0):
+ *   fwd: batch mean / biased variance per channel, y = relu?(gamma (x - mean) invstd + beta); mean and invstd [C] are
+ *        returned for the backward; running_mean / running_var (nullable) get torch's momentum update (unbiased var)
+ *   bwd: g = dy [y > 0];  dbeta = sum g;  dgamma = sum g xhat;  dx = gamma invstd (g - mean(g) - xhat mean(g xhat))
+ * gamma / beta may be NULL (affine=False).  workspace: dev, mvster_bn_train_workspace_bytes(N, C, S) bytes, 8-byte aligned.
+ * Partial sums are kept per (plane, chunk) in double and summed in a fixed order: bit-reproducible. */
+long long mvster_bn_train_workspace_bytes(int N, int C, long long S);
+int mvster_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                        float* running_mean, float* running_var, float momentum, float eps, int relu, int N, int C,
+                        long long S, void* workspace, void* stream);
+int mvster_bn_train_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* mean,
+                        const float* invstd, float* dx, float* dgamma, float* dbeta, int relu, int N, int C, long long S,
+                        void* workspace, void* stream);
+
 /* ---- homo_warping compatibility (models/mvs4net_utils.py:21-67): materialises [B, C, D, H, W] fp32 -------- */
 int mvster_homo_warp(const void* src, const float* rt /* dev [B,12] */, const float* hypo, float* warped, int B,
                      int C, int D, int H, int W, int Hs, int Ws, int dtype, void* stream);

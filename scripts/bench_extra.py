@@ -530,12 +530,20 @@ def bench_train_step(args, dev):
 
     res = {"bench": "train_step_mvs4net_512x640_b2_n5", "config": "fwd + OT loss (10 iters) + bwd + Adam, fp32 (TF32 off)"}
     its = max(3, args.iters // 4)
-    for name, eager in (("b200", False), ("eager_reference_like", True)):
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as NW
+    # fused training-mode BatchNorm + ReLU of the regulariser (mvster_bn_train_*) on / off, cuDNN TF32 off / on
+    for name, eager, fused_bn, tf32 in (("b200", False, True, False), ("b200_cudnn_batchnorm", False, False, False),
+                                        ("eager_reference_like", True, False, False), ("b200_tf32", False, True, True),
+                                        ("b200_cudnn_batchnorm_tf32", False, False, True)):
         model.stagenet = _EagerStagenet() if eager else fused_stagenet
+        NW.FUSED_TRAIN_BATCHNORM = fused_bn
+        torch.backends.cudnn.allow_tf32 = tf32
         torch.cuda.reset_peak_memory_stats()
         res[name + "_ms"] = timed(lambda: step(eager), its)
         res[name + "_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
     model.stagenet = fused_stagenet
+    NW.FUSED_TRAIN_BATCHNORM = True
+    torch.backends.cudnn.allow_tf32 = False
     res["samples_per_s_b200"] = 1e3 * b / res["b200_ms"]
     res["speedup"] = res["eager_reference_like_ms"] / res["b200_ms"]
     print(json.dumps(res))

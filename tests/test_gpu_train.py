@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import deep_reconstruction_with_epipolar_lines_mvster_b200 as mv
-from deep_reconstruction_with_epipolar_lines_mvster_b200 import loss as L, synthetic as syn
+from deep_reconstruction_with_epipolar_lines_mvster_b200 import loss as L, ops, synthetic as syn
 
 from test_network_host import CFG
 
@@ -88,3 +88,72 @@ def test_training_steps_reduce_the_loss(golden):
         opt.step()
         first = float(total.detach()) if first is None else first
     assert float(total.detach()) < first - 1e-3, (first, float(total.detach()))
+
+
+@pytest.mark.parametrize("shape,relu", [((2, 8, 4, 16, 20), True), ((2, 16, 8, 6, 10), True), ((3, 64, 4, 5, 4), False),
+                                        ((2, 8, 4, 64, 80), True), ((1, 32, 136, 100), True)])
+def test_fused_training_batchnorm_matches_torch(shape, relu):
+    """``mvster_bn_train_fwd`` / ``mvster_bn_train_bwd`` against nn.BatchNorm + ReLU in float64: output, running
+    statistics, num_batches_tracked, gradients of x / weight / bias (tolerances: 2e-5 of the range)."""
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as N
+    torch.manual_seed(sum(shape))
+    cls = torch.nn.BatchNorm3d if len(shape) == 5 else torch.nn.BatchNorm2d
+    x = (torch.randn(shape) * 2.0 + 0.7)
+    gout = torch.randn(shape)
+    ref_bn = cls(shape[1]).double().train()
+    with torch.no_grad():
+        ref_bn.weight.copy_(torch.rand(shape[1]) + 0.5)
+        ref_bn.bias.copy_(torch.randn(shape[1]) * 0.3)
+    bn = cls(shape[1]).train()
+    bn.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in ref_bn.state_dict().items()})
+    bn = bn.to(DEV)
+    xr = x.double().requires_grad_(True)
+    yr = ref_bn(xr)
+    yr = torch.relu(yr) if relu else yr
+    (yr * gout.double()).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    launches = mv.launch_count()
+    yg = N.bn_act(bn, xg, relu)
+    assert mv.launch_count() - launches == 3                       # the fused kernels ran, not cuDNN
+    (yg * gout.to(DEV)).sum().backward()
+    assert mv.launch_count() - launches == 6
+    tol = lambda t: 2e-5 * max(1.0, float(t.abs().max()))
+    assert (yg.detach().cpu().double() - yr.detach()).abs().max().item() < tol(yr)
+    assert (xg.grad.cpu().double() - xr.grad).abs().max().item() < tol(xr.grad)
+    assert (bn.weight.grad.cpu().double() - ref_bn.weight.grad).abs().max().item() < 1e-4 * max(1.0, float(ref_bn.weight.grad.abs().max()))
+    assert (bn.bias.grad.cpu().double() - ref_bn.bias.grad).abs().max().item() < 1e-4 * max(1.0, float(ref_bn.bias.grad.abs().max()))
+    assert (bn.running_mean.cpu().double() - ref_bn.running_mean).abs().max().item() < 1e-6
+    assert (bn.running_var.cpu().double() - ref_bn.running_var).abs().max().item() < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+    # bit-reproducible: fixed-order partial sums, no atomics
+    xg2 = x.to(DEV).requires_grad_(True)
+    yg2 = N.bn_act(bn, xg2, relu)
+    (yg2 * gout.to(DEV)).sum().backward()
+    assert torch.equal(yg2, yg) and torch.equal(xg2.grad, xg.grad)
+
+
+def test_fused_training_batchnorm_falls_back_where_it_does_not_apply():
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as N
+    bn = torch.nn.BatchNorm2d(8).to(DEV).train()
+    x = torch.randn(2, 8, 6, 10, device=DEV).contiguous(memory_format=torch.channels_last)
+    launches = mv.launch_count()
+    y = N.bn_act(bn, x, True)                                      # channels_last: cuDNN's NHWC kernels
+    assert mv.launch_count() == launches and y.shape == x.shape
+    bn.eval()
+    y = N.bn_act(bn, torch.randn(2, 8, 6, 10, device=DEV), True)   # eval: running statistics
+    assert mv.launch_count() == launches
+    with pytest.raises(RuntimeError):
+        ops.bn_train_fwd(torch.randn(2, 8, 3, 3, device=DEV), None, None, None, None, 0.1, 1e-5, True)   # plane of 9
+
+
+def test_training_step_with_and_without_fused_batchnorm_agree(golden):
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as N
+    g = golden("train")
+    totals = []
+    for fused in (True, False):
+        N.FUSED_TRAIN_BATCHNORM = fused
+        try:
+            totals.append(float(_step(g)[2].detach()))
+        finally:
+            N.FUSED_TRAIN_BATCHNORM = True
+    assert abs(totals[0] - totals[1]) < 2e-3 * abs(totals[1]), totals
