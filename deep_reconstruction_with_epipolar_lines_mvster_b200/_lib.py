@@ -53,6 +53,10 @@ _SIGNATURES = {
     "mvster_bn_train_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_int, c_int,
                                     ctypes.c_longlong, _P, _P]),
     "mvster_bn_train_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, ctypes.c_longlong, _P, _P]),
+    "mvster_conv3d_wgrad_workspace_bytes": (ctypes.c_longlong, [c_int] * 7),
+    "mvster_conv3d_wgrad": (c_int, [_P, _P, _P] + [c_int] * 10 + [_P, _P]),
+    "mvster_conv1x1_wgrad_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, ctypes.c_longlong]),
+    "mvster_conv1x1_wgrad": (c_int, [_P, _P, _P, _P, c_int, c_int, ctypes.c_longlong, _P, _P]),
     "mvster_tail_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "mvster_geo_check_pair": (c_int, [_P, POINTER(c_double), POINTER(c_double), _P, POINTER(c_double),
                                       POINTER(c_double), c_double, c_double, _P, _P, _P, _P, c_int, c_int, _P]),

@@ -67,6 +67,89 @@ def bn_act(bn: nn.modules.batchnorm._BatchNorm, x: torch.Tensor, relu: bool) -> 
     return F.relu(y, inplace=True) if relu else y
 
 
+class _Conv3dHandWgrad(torch.autograd.Function):
+    """``conv(x)`` of a bias-free ``nn.Conv3d`` / ``nn.ConvTranspose3d`` of the regulariser: cuDNN forward and data
+    gradient, the weight gradient on ``ops.conv3d_wgrad`` (cuDNN's few-channel 3-D wgrad kernels were the largest
+    entry of a training step)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, conv):
+        ctx.conv = conv
+        ctx.save_for_backward(x, weight)
+        return conv._conv_forward(x, weight, None) if isinstance(conv, nn.Conv3d) else \
+            F.conv_transpose3d(x, weight, None, conv.stride, conv.padding, conv.output_padding, 1, conv.dilation)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        conv = ctx.conv
+        transposed = isinstance(conv, nn.ConvTranspose3d)
+        gy = gy.contiguous()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.ops.aten.convolution_backward(gy, x, weight, None, list(conv.stride), list(conv.padding),
+                                                     list(conv.dilation), transposed, list(conv.output_padding), 1,
+                                                     [True, False, False])[0]
+        gw = None
+        if ctx.needs_input_grad[1]:
+            a, b = (x, gy) if transposed else (gy, x)
+            gw = ops.conv3d_wgrad(a, b, conv.kernel_size[0], conv.stride[1])
+        return gx, gw, None
+
+
+class _ProbHandWgrad(torch.autograd.Function):
+    """``prob(x)`` (``nn.Conv3d(8, 1, 1)`` with bias): stock forward, ``grad_x = grad_out * w`` as a broadcast product,
+    weight and bias gradient on ``ops.conv1x1_wgrad`` (one streaming pass)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return F.conv3d(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gy * weight.view(1, -1, 1, 1, 1) if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = ops.conv1x1_wgrad(x, gy)
+            gw, gb = dw.view_as(weight), db
+        return gx, gw, gb
+
+
+def prob_train(conv: nn.Conv3d, x):
+    if (HAND_WGRAD3D and conv.training and torch.is_grad_enabled() and conv.weight.requires_grad and conv.bias is not None
+            and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous() and x.shape[1] == 8
+            and conv.out_channels == 1 and tuple(conv.kernel_size) == (1, 1, 1) and tuple(conv.stride) == (1, 1, 1)
+            and tuple(conv.padding) == (0, 0, 0) and x[0, 0].numel() % 4 == 0 and x.data_ptr() % 16 == 0):
+        return _ProbHandWgrad.apply(x, conv.weight, conv.bias)
+    return conv(x)
+
+
+def _hand_wgrad_applies(conv, x) -> bool:
+    if not (HAND_WGRAD3D and torch.is_grad_enabled() and conv.weight.requires_grad and conv.bias is None
+            and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous()
+            and conv.weight.dtype == torch.float32 and conv.groups == 1 and tuple(conv.dilation) == (1, 1, 1)):
+        return False
+    kd, kh, kw = conv.kernel_size
+    st = tuple(conv.stride)
+    if (kh, kw) != (3, 3) or kd not in (1, 3) or tuple(conv.padding) != (kd // 2, 1, 1) or st[0] != 1 or st[1] != st[2]:
+        return False
+    if isinstance(conv, nn.ConvTranspose3d):
+        return (st[1] == 2 and kd == 1 and tuple(conv.output_padding) == (0, 1, 1) and conv.in_channels % 8 == 0)
+    return isinstance(conv, nn.Conv3d) and st[1] in (1, 2) and conv.out_channels % 8 == 0 and conv.padding_mode == "zeros"
+
+
+def conv3d_train(conv, x):
+    """``conv(x)`` with the hand-written weight gradient where it applies (training, planar fp32 CUDA, the
+    regulariser's kernel shapes); the stock module call otherwise."""
+    if conv.training and _hand_wgrad_applies(conv, x):
+        return _Conv3dHandWgrad.apply(x, conv.weight, conv)
+    return conv(x)
+
+
+HAND_WGRAD3D = True  # module switch (tests / A-B timing): False = cuDNN's weight gradient for the 3-D convolutions
 FUSED_TRAIN_BATCHNORM = True  # module switch (tests / A-B timing): False = stock nn.BatchNorm + F.relu in training
 
 
@@ -311,7 +394,7 @@ class ConvBnReLU3D(nn.Module):
         self.bn = nn.BatchNorm3d(cout)
 
     def forward(self, x):
-        return bn_act(self.bn, self.conv(x), True)
+        return bn_act(self.bn, conv3d_train(self.conv, x), True)
 
 
 def _up3d(cin, cout):
@@ -355,7 +438,7 @@ class reg2d(_FoldedWeights, nn.Module):
     @staticmethod
     def _up(seq: nn.Sequential, x):
         """``_up3d`` block (ConvTranspose3d, BatchNorm3d, ReLU) with the BatchNorm + ReLU pair through ``bn_act``."""
-        return bn_act(seq[1], seq[0](x), True)
+        return bn_act(seq[1], conv3d_train(seq[0], x), True)
 
     def _trunk(self, x):
         conv0 = self.conv0(x)
@@ -369,7 +452,7 @@ class reg2d(_FoldedWeights, nn.Module):
     def forward(self, x):
         conv0, x = self._trunk(x)
         x = conv0 + self._up(self.conv11, x)
-        return self.prob(x).squeeze(1)
+        return prob_train(self.prob, x).squeeze(1)
 
     # ---- fused last layers + tail -----------------------------------------------------------------------------------
     def fused_tail_supported(self) -> bool:

@@ -684,6 +684,50 @@ def bn_train_bwd(x: torch.Tensor, y: torch.Tensor, dy: torch.Tensor, weight, mea
     return dx, dw, db
 
 
+def conv3d_wgrad_supported(a: torch.Tensor, b: torch.Tensor, kd: int, stride: int) -> bool:
+    """Planar fp32 CUDA ``[N,C,D,H,W]`` pair of ``conv3d_wgrad`` (A channels % 8 == 0, matching spatial sizes)."""
+    if not (a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.float32 and a.dim() == b.dim() == 5):
+        return False
+    if kd not in (1, 3) or stride not in (1, 2) or a.shape[1] % 8 or a.shape[0] != b.shape[0] or a.shape[2] != b.shape[2]:
+        return False
+    ha, wa, hb, wb = a.shape[3], a.shape[4], b.shape[3], b.shape[4]
+    if stride == 1:
+        return (ha, wa) == (hb, wb)
+    return ((hb + 1) // 2, (wb + 1) // 2) == (ha, wa)
+
+
+def conv3d_wgrad(a: torch.Tensor, b: torch.Tensor, kd: int, stride: int) -> torch.Tensor:
+    """``mvster_conv3d_wgrad``: ``dW [CA,CB,kd,3,3] = sum A[n,a,d,y,x] B[n,b,d+kd-kd//2, s*y+ky-1, s*x+kx-1]``.
+    Conv3d: ``a = grad_output``, ``b = input``; ConvTranspose3d (stride 2): ``a = input``, ``b = grad_output``."""
+    a, b = _f32c(a, "A"), _f32c(b, "B")
+    if not conv3d_wgrad_supported(a, b, kd, stride):
+        raise RuntimeError("conv3d_wgrad: unsupported shapes A %s B %s kd=%d stride=%d" % (tuple(a.shape), tuple(b.shape), kd, stride))
+    n, ca, d, ha, wa = a.shape
+    cb, hb, wb = b.shape[1], b.shape[3], b.shape[4]
+    lib = _lib.load()
+    ws = torch.empty(((int(lib.mvster_conv3d_wgrad_workspace_bytes(n, ca, cb, kd, d, ha, wa)) + 3) // 4,), device=a.device,
+                     dtype=torch.float32)
+    dw = torch.empty((ca, cb, kd, 3, 3), device=a.device, dtype=torch.float32)
+    _lib.check(lib.mvster_conv3d_wgrad(_ptr(a), _ptr(b), _ptr(dw), n, ca, cb, kd, d, ha, wa, hb, wb, stride, _ptr(ws),
+                                       _stream(a)))
+    return dw
+
+
+def conv1x1_wgrad(x: torch.Tensor, g: torch.Tensor):
+    """``mvster_conv1x1_wgrad``: ``(dw [C], db [1])`` of a C -> 1 pointwise convolution, ``x`` [N,C,...], ``g`` [N,1,...]."""
+    x, g = _f32c(x, "x"), _f32c(g, "grad_output")
+    n, c = x.shape[0], x.shape[1]
+    s = x[0, 0].numel()
+    if g.shape[0] != n or g.shape[1] != 1 or g[0, 0].numel() != s:
+        raise RuntimeError("conv1x1_wgrad: grad_output %s does not match x %s" % (tuple(g.shape), tuple(x.shape)))
+    lib = _lib.load()
+    ws = torch.empty(((int(lib.mvster_conv1x1_wgrad_workspace_bytes(n, c, s)) + 7) // 8,), device=x.device, dtype=torch.float64)
+    dw = torch.empty((c,), device=x.device, dtype=torch.float32)
+    db = torch.empty((1,), device=x.device, dtype=torch.float32)
+    _lib.check(lib.mvster_conv1x1_wgrad(_ptr(x), _ptr(g), _ptr(dw), _ptr(db), n, c, s, _ptr(ws), _stream(x)))
+    return dw, db
+
+
 def tail_bwd(attn, hypo, depth, g_attn, g_depth, depth_mode: int) -> torch.Tensor:
     b, d, h, w = attn.shape
     g_attn = None if g_attn is None else _f32c(g_attn, "grad attn")

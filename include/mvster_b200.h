@@ -134,6 +134,24 @@ int mvster_bn_train_bwd(const float* x, const float* y, const float* dy, const f
                         const float* invstd, float* dx, float* dgamma, float* dbeta, int relu, int N, int C, long long S,
                         void* workspace, void* stream);
 
+/* ---- weight gradient of the regulariser's 3-D convolutions (training mode) -----------------------------------------
+ * Autograd of nn.Conv3d / nn.ConvTranspose3d inside ConvBnReLU3D / Deconv3d (models/mvs4net_utils.py:123-130, 884-926):
+ *     dW[a][b][kd][ky][kx] = sum_{n,d,y,x} A[n,a,d,y,x] * B[n,b, d+kd-KD/2, s*y+ky-1, s*x+kx-1]     (B zero outside)
+ *   Conv3d, kernel (KD,3,3), padding (KD/2,1,1), stride (1,s,s): A = grad_output [N,Cout,D,HA,WA], B = input [N,Cin,D,HB,WB]
+ *   ConvTranspose3d, kernel (1,3,3), padding (0,1,1), output_padding (0,1,1), stride (1,2,2):
+ *                                                     A = input [N,Cin,D,HA,WA], B = grad_output [N,Cout,D,2HA,2WA], s = 2
+ * dW is written in PyTorch's weight layout ([CA,CB,KD,3,3]).  KD in {1,3}, s in {1,2}, CA % 8 == 0, planar fp32.
+ * workspace: dev, mvster_conv3d_wgrad_workspace_bytes(...) bytes.  Bit-reproducible (fixed-order partial sums). */
+long long mvster_conv3d_wgrad_workspace_bytes(int N, int CA, int CB, int KD, int D, int HA, int WA);
+int mvster_conv3d_wgrad(const float* A, const float* B, float* dw, int N, int CA, int CB, int KD, int D, int HA, int WA,
+                        int HB, int WB, int stride, void* workspace, void* stream);
+
+/* Weight and bias gradient of the regulariser's last layer, prob = nn.Conv3d(8, 1, 1) (models/mvs4net_utils.py:914):
+ *   dw[c] = sum_{n,s} x[n,c,s] g[n,0,s],  db[0] = sum g  (db nullable);  x [N,8,S], g [N,1,S] planar fp32, S % 4 == 0. */
+long long mvster_conv1x1_wgrad_workspace_bytes(int N, int C, long long S);
+int mvster_conv1x1_wgrad(const float* x, const float* g, float* dw, float* db, int N, int C, long long S,
+                         void* workspace, void* stream);
+
 /* ---- homo_warping compatibility (models/mvs4net_utils.py:21-67): materialises [B, C, D, H, W] fp32 -------- */
 int mvster_homo_warp(const void* src, const float* rt /* dev [B,12] */, const float* hypo, float* warped, int B,
                      int C, int D, int H, int W, int Hs, int Ws, int dtype, void* stream);

@@ -531,16 +531,22 @@ def bench_train_step(args, dev):
     res = {"bench": "train_step_mvs4net_512x640_b2_n5", "config": "fwd + OT loss (10 iters) + bwd + Adam, fp32 (TF32 off)"}
     its = max(3, args.iters // 4)
     from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as NW
-    # fused training-mode BatchNorm + ReLU of the regulariser (mvster_bn_train_*) on / off, cuDNN TF32 off / on
-    for name, eager, fused_bn, tf32 in (("b200", False, True, False), ("b200_cudnn_batchnorm", False, False, False),
-                                        ("eager_reference_like", True, False, False), ("b200_tf32", False, True, True),
-                                        ("b200_cudnn_batchnorm_tf32", False, False, True)):
+    # hand-written training kernels of the regulariser on / off (fused BatchNorm + ReLU: mvster_bn_train_*; weight
+    # gradient of the 3-D convolutions: mvster_conv3d_wgrad), cuDNN TF32 off / on, cudnn.benchmark as train_mvs4.py sets it
+    torch.backends.cudnn.benchmark = True
+    for name, eager, fused_bn, hand_wgrad, tf32 in (
+            ("b200", False, True, True, False), ("b200_cudnn_wgrad", False, True, False, False),
+            ("b200_cudnn_wgrad_batchnorm", False, False, False, False), ("eager_reference_like", True, False, False, False),
+            ("b200_tf32", False, True, True, True), ("b200_cudnn_wgrad_tf32", False, True, False, True),
+            ("b200_cudnn_wgrad_batchnorm_tf32", False, False, False, True)):
         model.stagenet = _EagerStagenet() if eager else fused_stagenet
         NW.FUSED_TRAIN_BATCHNORM = fused_bn
+        NW.HAND_WGRAD3D = hand_wgrad
         torch.backends.cudnn.allow_tf32 = tf32
         torch.cuda.reset_peak_memory_stats()
         res[name + "_ms"] = timed(lambda: step(eager), its)
         res[name + "_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
+    NW.HAND_WGRAD3D = True
     model.stagenet = fused_stagenet
     NW.FUSED_TRAIN_BATCHNORM = True
     torch.backends.cudnn.allow_tf32 = False

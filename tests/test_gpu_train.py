@@ -157,3 +157,78 @@ def test_training_step_with_and_without_fused_batchnorm_agree(golden):
         finally:
             N.FUSED_TRAIN_BATCHNORM = True
     assert abs(totals[0] - totals[1]) < 2e-3 * abs(totals[1]), totals
+
+
+@pytest.mark.parametrize("cin,cout,kd,stride,transposed,d,h,w", [
+    (4, 8, 1, 1, False, 4, 16, 40), (8, 16, 1, 2, False, 3, 18, 70), (8, 16, 1, 2, False, 2, 17, 33),
+    (16, 16, 3, 1, False, 4, 9, 35), (32, 64, 1, 2, False, 2, 8, 12), (64, 64, 3, 1, False, 3, 5, 6),
+    (64, 32, 1, 2, True, 2, 6, 10), (16, 8, 1, 2, True, 4, 70, 36)])
+def test_conv3d_hand_wgrad_matches_torch_autograd(cin, cout, kd, stride, transposed, d, h, w):
+    """``mvster_conv3d_wgrad`` through ``network.conv3d_train`` against float64 autograd of the same layer: weight
+    gradient (2e-5 of its range), data gradient and output (cuDNN, fp32)."""
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as N
+    torch.manual_seed(cin * 7 + cout + kd + h)
+    if transposed:
+        conv = torch.nn.ConvTranspose3d(cin, cout, (1, 3, 3), padding=(0, 1, 1), output_padding=(0, 1, 1), stride=(1, 2, 2), bias=False)
+    else:
+        conv = torch.nn.Conv3d(cin, cout, (kd, 3, 3), stride=(1, stride, stride), padding=(kd // 2, 1, 1), bias=False)
+    x = torch.randn(2, cin, d, h, w)
+    import copy
+    conv64 = copy.deepcopy(conv).double()
+    xr = x.double().requires_grad_(True)
+    yr = conv64(xr)
+    gout = torch.randn(yr.shape)
+    (yr * gout.double()).sum().backward()
+    conv = conv.to(DEV).train()
+    xg = x.to(DEV).requires_grad_(True)
+    launches = mv.launch_count()
+    yg = N.conv3d_train(conv, xg)
+    (yg * gout.to(DEV)).sum().backward()
+    assert mv.launch_count() - launches == 2                       # wgrad + reduce ran
+    assert (yg.detach().cpu().double() - yr.detach()).abs().max().item() < 1e-4 * max(1.0, float(yr.abs().max()))
+    gw, gwr = conv.weight.grad.cpu().double(), conv64.weight.grad
+    assert gw.shape == gwr.shape
+    assert (gw - gwr).abs().max().item() < 2e-5 * max(1.0, float(gwr.abs().max())), (gw - gwr).abs().max().item()
+    assert (xg.grad.cpu().double() - xr.grad).abs().max().item() < 1e-4 * max(1.0, float(xr.grad.abs().max()))
+    # reproducible bit for bit
+    conv.weight.grad = None
+    xg2 = x.to(DEV).requires_grad_(True)
+    (N.conv3d_train(conv, xg2) * gout.to(DEV)).sum().backward()
+    assert torch.equal(conv.weight.grad.cpu().double(), gw)
+
+
+def test_training_step_with_and_without_hand_wgrad_agree(golden):
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as N
+    g = golden("train")
+    grads = []
+    for hand in (True, False):
+        N.HAND_WGRAD3D = hand
+        try:
+            model = _step(g)[0]
+            grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None and ".reg." in "." + k})
+        finally:
+            N.HAND_WGRAD3D = True
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 20
+    for k in grads[0]:
+        a, b = grads[0][k], grads[1][k]
+        # prob.bias has a mathematically zero gradient (softmax ignores a constant shift): absolute floor for it
+        assert (a - b).norm().item() <= 1e-3 * b.norm().item() + 1e-6, k
+
+
+def test_prob_hand_wgrad_matches_torch_autograd():
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as N
+    import copy
+    torch.manual_seed(3)
+    conv = torch.nn.Conv3d(8, 1, 1)
+    x, gout = torch.randn(2, 8, 4, 18, 22), torch.randn(2, 1, 4, 18, 22)
+    c64 = copy.deepcopy(conv).double()
+    xr = x.double().requires_grad_(True)
+    (c64(xr) * gout.double()).sum().backward()
+    conv = conv.to(DEV).train()
+    xg = x.to(DEV).requires_grad_(True)
+    launches = mv.launch_count()
+    (N.prob_train(conv, xg) * gout.to(DEV)).sum().backward()
+    assert mv.launch_count() - launches == 2
+    assert (conv.weight.grad.cpu().double() - c64.weight.grad).abs().max().item() < 2e-5 * max(1.0, float(c64.weight.grad.abs().max()))
+    assert (conv.bias.grad.cpu().double() - c64.bias.grad).abs().max().item() < 2e-5 * max(1.0, float(c64.bias.grad.abs().max()))
+    assert (xg.grad.cpu().double() - xr.grad).abs().max().item() < 1e-6
