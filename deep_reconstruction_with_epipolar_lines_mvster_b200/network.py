@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -149,8 +151,9 @@ def conv3d_train(conv, x):
     return conv(x)
 
 
-HAND_WGRAD3D = True  # module switch (tests / A-B timing): False = cuDNN's weight gradient for the 3-D convolutions
-FUSED_TRAIN_BATCHNORM = True  # module switch (tests / A-B timing): False = stock nn.BatchNorm + F.relu in training
+# module switches (tests / A-B timing; the environment variables set the initial value)
+HAND_WGRAD3D = os.environ.get("MVSTER_TRAIN_CUDNN_WGRAD") is None  # False = cuDNN's weight gradient for the 3-D convolutions
+FUSED_TRAIN_BATCHNORM = os.environ.get("MVSTER_TRAIN_CUDNN_BATCHNORM") is None  # module switch (tests / A-B timing): False = stock nn.BatchNorm + F.relu in training
 
 
 class Conv2d(nn.Module):
