@@ -25,6 +25,9 @@
 
 namespace mvster {
 
+#ifndef MVSTER_LIN_PY8
+#define MVSTER_LIN_PY8 1
+#endif
 constexpr int kLinTW = 32;      // output tile width; height 8 * PY (a thread owns PY vertically adjacent pixels)
 constexpr int kLinRC = 20;      // coarse columns held per CTA
 constexpr int kLinLW = 36;      // lateral tile row stride
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kLinThreads, (CO == 8 && PY == 1) ? 3 : 2) fpn
 template <int CL, int CO, typename OutT>
 static int launch_lin(const float* P, int pc, int poff, const float* lat, void* feat, const float* wc, const float* bc,
                       int B, int H, int W, cudaStream_t s) {
-    constexpr int PY = 1;  // pixels per thread; 2 (tile 32 x 16, weights shared) measured slower: 0.71 vs 0.55 ms at (8,8) - occupancy
+    constexpr int PY = (CO == 8) ? MVSTER_LIN_PY8 : 1;  // pixels per thread; 2 (tile 32 x 16, weights shared) measured slower at (8,8): two CTAs per SM
     using Gm = LinGeom<CL, CO, PY>;
     static thread_local LinParams<CL, CO> p;
     static_assert(sizeof(LinParams<CL, CO>) <= 32000, "weights must fit the kernel-parameter space");
