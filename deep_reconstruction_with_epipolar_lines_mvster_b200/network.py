@@ -129,6 +129,46 @@ def prob_train(conv: nn.Conv3d, x):
     return conv(x)
 
 
+class _Conv2dHandWgrad(torch.autograd.Function):
+    """``conv(x)`` of a bias-free 3x3 stride-1 ``nn.Conv2d`` of FPN4 in training: cuDNN forward and data gradient in
+    whatever memory format the activations have (channels_last in ``MVS4net.train()``), the weight gradient on
+    ``ops.conv3d_wgrad`` over planar copies of ``x`` and ``grad_output`` (D = 1)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, conv):
+        ctx.conv = conv
+        ctx.save_for_backward(x, weight)
+        return conv._conv_forward(x, weight, None)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        conv = ctx.conv
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.ops.aten.convolution_backward(gy, x, weight, None, list(conv.stride), list(conv.padding),
+                                                     list(conv.dilation), False, [0, 0], 1, [True, False, False])[0]
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = ops.conv3d_wgrad(gy.contiguous().unsqueeze(2), x.contiguous().unsqueeze(2), 1, 1).squeeze(2)
+            if weight.dim() == 4 and not weight.is_contiguous() and weight.is_contiguous(memory_format=torch.channels_last):
+                gw = gw.contiguous(memory_format=torch.channels_last)
+        return gx, gw, None
+
+
+def conv2d_train(conv: nn.Conv2d, x):
+    """``conv(x)`` with the hand-written weight gradient for FPN4's 3x3 stride-1 layers in training mode - only while
+    cuDNN is held to fp32 (``torch.backends.cudnn.allow_tf32 = False``): measured per training step, the fp32 hand-written
+    kernel beats cuDNN's fp32 NHWC weight gradient (10.8 -> 5.4 + 2.6 ms) and loses to its TF32 one (44.6 vs 39.0 ms)."""
+    if (HAND_WGRAD2D and not torch.backends.cudnn.allow_tf32 and conv.training and torch.is_grad_enabled() and conv.weight.requires_grad and conv.bias is None
+            and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and conv.weight.dtype == torch.float32
+            and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (1, 1)
+            and tuple(conv.dilation) == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
+            and conv.out_channels % 8 == 0):
+        return _Conv2dHandWgrad.apply(x, conv.weight, conv)
+    return conv(x)
+
+
 def _hand_wgrad_applies(conv, x) -> bool:
     if not (HAND_WGRAD3D and torch.is_grad_enabled() and conv.weight.requires_grad and conv.bias is None
             and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous()
@@ -153,6 +193,7 @@ def conv3d_train(conv, x):
 
 # module switches (tests / A-B timing; the environment variables set the initial value)
 HAND_WGRAD3D = os.environ.get("MVSTER_TRAIN_CUDNN_WGRAD") is None  # False = cuDNN's weight gradient for the 3-D convolutions
+HAND_WGRAD2D = os.environ.get("MVSTER_TRAIN_CUDNN_WGRAD2D") is None and HAND_WGRAD3D  # the same for FPN4's 3x3 layers
 FUSED_TRAIN_BATCHNORM = os.environ.get("MVSTER_TRAIN_CUDNN_BATCHNORM") is None  # module switch (tests / A-B timing): False = stock nn.BatchNorm + F.relu in training
 
 
@@ -166,7 +207,7 @@ class Conv2d(nn.Module):
         self.relu = relu
 
     def forward(self, x):
-        return bn_act(self.bn, self.conv(x), self.relu)
+        return bn_act(self.bn, conv2d_train(self.conv, x), self.relu)
 
 
 class _FoldedWeights:
@@ -380,11 +421,11 @@ class FPN4(_FoldedWeights, nn.Module):
         top = self.conv3(c2)
         out = {"stage1": self.out1(top)}
         top = self._up(top) + self.inner1(c2)
-        out["stage2"] = self.out2(top)
+        out["stage2"] = conv2d_train(self.out2, top)
         top = self._up(top) + self.inner2(c1)
-        out["stage3"] = self.out3(top)
+        out["stage3"] = conv2d_train(self.out3, top)
         top = self._up(top) + self.inner3(c0)
-        out["stage4"] = self.out4(top)
+        out["stage4"] = conv2d_train(self.out4, top)
         return out
 
 

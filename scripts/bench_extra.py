@@ -541,12 +541,12 @@ def bench_train_step(args, dev):
             ("b200_cudnn_wgrad_batchnorm_tf32", False, False, False, True)):
         model.stagenet = _EagerStagenet() if eager else fused_stagenet
         NW.FUSED_TRAIN_BATCHNORM = fused_bn
-        NW.HAND_WGRAD3D = hand_wgrad
+        NW.HAND_WGRAD3D = NW.HAND_WGRAD2D = hand_wgrad
         torch.backends.cudnn.allow_tf32 = tf32
         torch.cuda.reset_peak_memory_stats()
         res[name + "_ms"] = timed(lambda: step(eager), its)
         res[name + "_peak_MB"] = torch.cuda.max_memory_allocated() / 1e6
-    NW.HAND_WGRAD3D = True
+    NW.HAND_WGRAD3D = NW.HAND_WGRAD2D = True
     model.stagenet = fused_stagenet
     NW.FUSED_TRAIN_BATCHNORM = True
     torch.backends.cudnn.allow_tf32 = False

@@ -202,12 +202,12 @@ def test_training_step_with_and_without_hand_wgrad_agree(golden):
     g = golden("train")
     grads = []
     for hand in (True, False):
-        N.HAND_WGRAD3D = hand
+        N.HAND_WGRAD3D = N.HAND_WGRAD2D = hand
         try:
             model = _step(g)[0]
-            grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None and ".reg." in "." + k})
+            grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
         finally:
-            N.HAND_WGRAD3D = True
+            N.HAND_WGRAD3D = N.HAND_WGRAD2D = True
     assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 20
     for k in grads[0]:
         a, b = grads[0][k], grads[1][k]
@@ -232,3 +232,36 @@ def test_prob_hand_wgrad_matches_torch_autograd():
     assert (conv.weight.grad.cpu().double() - c64.weight.grad).abs().max().item() < 2e-5 * max(1.0, float(c64.weight.grad.abs().max()))
     assert (conv.bias.grad.cpu().double() - c64.bias.grad).abs().max().item() < 2e-5 * max(1.0, float(c64.bias.grad.abs().max()))
     assert (xg.grad.cpu().double() - xr.grad).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("cin,cout,h,w,cl", [(3, 8, 20, 36, True), (16, 16, 9, 33, True), (64, 32, 6, 10, False), (64, 8, 12, 40, True)])
+def test_conv2d_hand_wgrad_matches_torch_autograd(cin, cout, h, w, cl):
+    """FPN4's 3x3 layers in training: weight gradient on ``mvster_conv3d_wgrad`` (D = 1) over planar copies, forward and
+    data gradient on cuDNN in the activations' own memory format (channels_last in ``MVS4net.train()``)."""
+    from deep_reconstruction_with_epipolar_lines_mvster_b200 import network as N
+    import copy
+    torch.manual_seed(cin + cout + h)
+    conv = torch.nn.Conv2d(cin, cout, 3, padding=1, bias=False)
+    x, c64 = torch.randn(2, cin, h, w), copy.deepcopy(conv).double()
+    xr = x.double().requires_grad_(True)
+    yr = c64(xr)
+    gout = torch.randn(yr.shape)
+    (yr * gout.double()).sum().backward()
+    conv = conv.to(DEV).train()
+    xg = x.to(DEV)
+    if cl:
+        conv = conv.to(memory_format=torch.channels_last)
+        xg = xg.contiguous(memory_format=torch.channels_last)
+    xg.requires_grad_(True)
+    launches = mv.launch_count()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                        # the hand-written 2-D path is the fp32-exact mode's
+    try:
+        (N.conv2d_train(conv, xg) * gout.to(DEV)).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert mv.launch_count() - launches == 2
+    gw = conv.weight.grad
+    assert gw.shape == conv.weight.shape and gw.stride() == conv.weight.stride()
+    assert (gw.cpu().double() - c64.weight.grad).abs().max().item() < 2e-5 * max(1.0, float(c64.weight.grad.abs().max()))
+    assert (xg.grad.cpu().double() - xr.grad).abs().max().item() < 1e-4 * max(1.0, float(xr.grad.abs().max()))
