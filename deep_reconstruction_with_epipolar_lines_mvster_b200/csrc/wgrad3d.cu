@@ -17,7 +17,8 @@
 namespace mvster {
 
 constexpr int kWgRows = 64;    // positions rows per warp task
-constexpr int kWgWarps = 4;    // warps per CTA: consecutive row chunks of the same (channel, plane) task
+constexpr int kWgWarps = 4;    // warps per CTA: four (B channel, A block, depth tap) tasks of the same position chunk, so
+                               // that small planes (one row chunk) still fill their CTAs and the warps share rows in L1
 constexpr int kWgABlk = 8;     // A channels per lane
 
 struct WgradParams {
@@ -31,12 +32,12 @@ struct WgradParams {
 template <int S>
 __global__ void __launch_bounds__(kWgWarps * 32) wgrad3d_kernel(const WgradParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // blockIdx.x: (x strip, group of kWgWarps row chunks); blockIdx.y: (b, a block, kd); blockIdx.z: n * D + d
+    // blockIdx.x: (x strip, row chunk); blockIdx.y * kWgWarps + warp: (b, a block, kd); blockIdx.z: n * D + d
     const int xs = blockIdx.x % p.nxstrip;
-    const int yc = (blockIdx.x / p.nxstrip) * kWgWarps + warp;
-    if (yc >= p.nychunk) return;
+    const int yc = blockIdx.x / p.nxstrip;
     const int nab = p.CA / kWgABlk;
-    int t = blockIdx.y;
+    int t = blockIdx.y * kWgWarps + warp;
+    if (t >= p.CB * nab * p.KD) return;
     const int kd = t % p.KD; t /= p.KD;
     const int ab = t % nab;
     const int b = t / nab;
@@ -229,13 +230,13 @@ extern "C" int mvster_conv3d_wgrad(const float* A, const float* B, float* dw, in
     long long nparts;
     wgrad_geometry(N, D, HA, WA, &nyc, &nxs, &nparts);
     const long long tasks = (long long)CB * (CA / kWgABlk) * KD;
-    if (tasks > 65535 || (long long)N * D > 65535 || nparts > 2147483647LL)
+    if ((tasks + kWgWarps - 1) / kWgWarps > 65535 || (long long)N * D > 65535 || nparts > 2147483647LL)
         return fail(MVSTER_ERR_UNSUPPORTED, "conv3d_wgrad: grid too large");
     DeviceGuard guard(dw);
     if (guard.status != MVSTER_OK) return guard.status;
     cudaStream_t s = (cudaStream_t)stream;
     WgradParams p{A, B, static_cast<float*>(workspace), N, CA, CB, KD, D, HA, WA, HB, WB, nyc, nxs};
-    dim3 grid(nxs * ((nyc + kWgWarps - 1) / kWgWarps), (unsigned)tasks, N * D);
+    dim3 grid(nxs * nyc, (unsigned)((tasks + kWgWarps - 1) / kWgWarps), N * D);
     if (stride == 1) wgrad3d_kernel<1><<<grid, kWgWarps * 32, 0, s>>>(p);
     else wgrad3d_kernel<2><<<grid, kWgWarps * 32, 0, s>>>(p);
     count_launch();
