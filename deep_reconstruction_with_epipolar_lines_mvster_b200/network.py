@@ -703,6 +703,7 @@ class GraphedMVS4net:
         self.depth_values = torch.ones((batch, 2), device=dev)
         self.graph = None
         self.out = None
+        self._stage, self._pending = None, False
 
     def _load(self, imgs, proj_matrices, depth_values):
         for dst, src in zip(self.imgs, imgs):
@@ -727,5 +728,49 @@ class GraphedMVS4net:
         if self.graph is None:
             self.capture(imgs, proj_matrices, depth_values)
         self._load(imgs, proj_matrices, depth_values)
+        self.graph.replay()
+        return self.out
+
+    # ---- pipelined serving: the next request's inputs are uploaded while the current one computes ---------------------
+    def prefetch(self, imgs, proj_matrices, depth_values):
+        """Start uploading the NEXT request (pinned host tensors, or device tensors) into staging buffers on a side
+        stream; returns immediately.  ``run_prefetched()`` consumes it.  While a forward runs (~6 ms per 832x1152 scene) the
+        57 MB of images per scene cross the link concurrently instead of in front of it."""
+        if self.graph is None:
+            self.capture(imgs, proj_matrices, depth_values)
+        dev = self.imgs[0].device
+        if self._stage is None:
+            self._stage = ([torch.empty_like(t) for t in self.imgs], {k: torch.empty_like(t) for k, t in self.proj.items()},
+                           torch.empty_like(self.depth_values))
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
+        s_imgs, s_proj, s_dv = self._stage
+        self._copy_stream.wait_event(self._consumed)      # the previous request has left the staging buffers
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(s_imgs, imgs):
+                dst.copy_(src, non_blocking=True)
+            for k, dst in s_proj.items():
+                dst.copy_(proj_matrices[k], non_blocking=True)
+            s_dv.copy_(depth_values[:, [0, -1]], non_blocking=True)
+            self._staged.record(self._copy_stream)
+        self._pending = True
+
+    def run_prefetched(self):
+        """Forward of the request handed to ``prefetch()``: staging -> graph inputs (device copy), one graph replay.
+        The returned tensors are graph-owned and valid until the next replay."""
+        if not self._pending:
+            raise RuntimeError("GraphedMVS4net.run_prefetched(): call prefetch(imgs, proj_matrices, depth_values) first")
+        dev = self.imgs[0].device
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(self._staged)
+        s_imgs, s_proj, s_dv = self._stage
+        for dst, src in zip(self.imgs, s_imgs):
+            dst.copy_(src, non_blocking=True)
+        for k, dst in self.proj.items():
+            dst.copy_(s_proj[k], non_blocking=True)
+        self.depth_values.copy_(s_dv, non_blocking=True)
+        self._consumed.record(cur)
+        self._pending = False
         self.graph.replay()
         return self.out

@@ -593,3 +593,29 @@ def test_mvs4net_teacher_forced_stages_attention_and_flip_fraction(golden, model
         assert err < (5e-4 if st == "stage4" else 1e-4), (st, err)
         assert fd == 0.0, (st, fd)
         assert flips < 1e-3, (st, flips)
+
+
+def test_graphed_network_pipelined_requests_match_plain_calls(model):
+    """``GraphedMVS4net.prefetch`` / ``run_prefetched`` (next request uploaded on a side stream while the current one
+    computes) return exactly what plain calls return, request by request, for alternating inputs from pinned memory."""
+    b, n, h0, w0 = 1, 3, 64, 128
+    gen = torch.Generator().manual_seed(4)
+    reqs = []
+    for i in range(3):
+        imgs = [torch.rand((b, 3, h0, w0), generator=gen).pin_memory() for _ in range(n)]
+        proj = {k: torch.from_numpy(v).pin_memory() for k, v in syn.proj_matrices_all_stages(b, n, h0, w0, per_batch_jitter=0.01 * i).items()}
+        reqs.append((imgs, proj, torch.from_numpy(syn.depth_values(b)).pin_memory()))
+    g = mv.GraphedMVS4net(model, b, n, h0, w0, DEV)
+    plain = [g(*r)["stage4"]["depth"].clone() for r in reqs]
+    assert not torch.equal(plain[0], plain[1])
+    with pytest.raises(RuntimeError):
+        mv.GraphedMVS4net(model, b, n, h0, w0, DEV).run_prefetched()
+    g.prefetch(*reqs[0])
+    got = []
+    for i in range(3):
+        out = g.run_prefetched()["stage4"]["depth"]
+        if i + 1 < 3:
+            g.prefetch(*reqs[i + 1])          # overlaps the replay that was just enqueued
+        got.append(out.clone())
+    for a, c in zip(plain, got):
+        assert torch.equal(a, c)
