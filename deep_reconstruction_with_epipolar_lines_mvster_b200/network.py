@@ -747,6 +747,9 @@ class GraphedMVS4net:
             self._consumed.record(torch.cuda.current_stream(dev))
         s_imgs, s_proj, s_dv = self._stage
         self._copy_stream.wait_event(self._consumed)      # the previous request has left the staging buffers
+        if any(t.is_cuda for t in list(imgs) + [depth_values]):
+            # device-resident inputs may still be being written on the caller's stream: order the side stream behind it
+            self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self._copy_stream):
             for dst, src in zip(s_imgs, imgs):
                 dst.copy_(src, non_blocking=True)
